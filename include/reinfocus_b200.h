@@ -1,0 +1,162 @@
+/* reinfocus_b200 C-ABI: the drop-in boundary of the B200-native reinfocus hot path.
+ *
+ * The reference (jeffwhunter/reinfocus) is pure Python + numba-CUDA and has no FFI of its
+ * own; the calls below are what a ctypes binding inside the reference's
+ * reinfocus/graphics/render.py and reinfocus/vision.py would bind instead of launching
+ * numba kernels / calling OpenCV (INTEGRATION.md shows that binding). Each entry point
+ * cites the reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types.
+ *   - every function returns 0 on success or a negative rf_status; rf_last_error() gives
+ *     the message of the last failure on that context (rf_last_global_error() for
+ *     failures without a context, e.g. in rf_create).
+ *   - "d_" pointers are device pointers on the context's GPU, owned by the caller (e.g.
+ *     torch CUDA tensors); "h_" pointers are host pointers (pinned memory makes the
+ *     copies asynchronous). The context owns only the RNG-state buffer, the packed scene
+ *     parameters and small scratch.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream). All
+ *     work is stream-ordered; functions documented as "synchronous" block the host until
+ *     their result is in host memory.
+ *   - a context is bound to one GPU and is not thread-safe; use one context per GPU.
+ */
+#ifndef REINFOCUS_B200_H
+#define REINFOCUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rf_ctx rf_ctx;
+
+typedef enum {
+    RF_OK = 0,
+    RF_ERR_INVALID = -1, /* bad argument / call order (maps to AssertionError in Python) */
+    RF_ERR_CUDA = -2,    /* CUDA runtime failure (maps to RuntimeError) */
+    RF_ERR_NOMEM = -3,
+    RF_ERR_NO_SCENE = -4 /* render before update_targets/update_focus_planes
+                            (reference graphics/device_data.py:43 AssertionError) */
+} rf_status;
+
+/* One xoroshiro128+ state, layout-identical to numba.cuda.random.xoroshiro128p_dtype. */
+typedef struct {
+    uint64_t s0;
+    uint64_t s1;
+} rf_rng_state;
+
+/* -------------------------------------------------------------------------------------
+ * Context
+ * ----------------------------------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device`. Replaces the implicit numba context that
+ * reference graphics/render.py:127-145 (FastRenderer.__init__) relies on. */
+int rf_create(rf_ctx **out, int device);
+int rf_destroy(rf_ctx *ctx);
+const char *rf_last_error(const rf_ctx *ctx);
+const char *rf_last_global_error(void);
+/* ABI version of this library (bumped on any signature change). */
+int rf_abi_version(void);
+/* Device facts the host side sizes launches and rooflines with. */
+int rf_device_info(const rf_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
+                   int *clock_khz);
+/* Number of kernels this context has launched since creation (bench "gpu_launches"). */
+int64_t rf_launch_count(const rf_ctx *ctx);
+
+/* -------------------------------------------------------------------------------------
+ * RNG states. Replaces reference graphics/random.py:8-18 (make_random_states ->
+ * numba.cuda.random.create_xoroshiro128p_states, a sequential CPU jump chain + H2D) and
+ * the cache policy of reference graphics/render.py:248-257 (_make_random_states).
+ * ----------------------------------------------------------------------------------- */
+
+/* Guarantees the context holds at least n_states states. If it holds fewer, ALL states
+ * are re-created from `seed` at the new size (reference render.py:256-257 re-seeds with 0
+ * on growth); otherwise the existing, already-advanced states are kept. */
+int rf_rng_ensure(rf_ctx *ctx, int64_t n_states, uint64_t seed, void *stream);
+/* Drops the cached states (next rf_rng_ensure re-creates them). */
+int rf_rng_reset(rf_ctx *ctx);
+int64_t rf_rng_count(const rf_ctx *ctx);
+/* Synchronous copies of states [first, first+n) to / from host memory (parity tests,
+ * checkpointing of env state - the reference cannot serialise its states). */
+int rf_rng_export(rf_ctx *ctx, rf_rng_state *h_dst, int64_t first, int64_t n);
+int rf_rng_import(rf_ctx *ctx, const rf_rng_state *h_src, int64_t first, int64_t n);
+/* Fills a caller-owned device buffer with create_xoroshiro128p_states(n, seed): state i
+ * is state 0 jumped i * 2**64 steps, computed in parallel by GF(2) matrix doubling. */
+int rf_rng_init_device(rf_ctx *ctx, rf_rng_state *d_states, int64_t n, uint64_t seed,
+                       void *stream);
+/* xoroshiro128p_uniform_float32 draws: out[i*draws + k] = k-th draw of state i (advances
+ * the caller's states). Test / API-parity helper for reference graphics/random.py:21-33. */
+int rf_rng_uniform_device(rf_ctx *ctx, rf_rng_state *d_states, int64_t n, int draws,
+                          float *d_out, void *stream);
+
+/* -------------------------------------------------------------------------------------
+ * Scene parameters. Replaces the device arrays built by reference
+ * graphics/world.py:100-123 (FastWorlds._make_device_data: float32 [n,2] = half side, z)
+ * and graphics/camera.py:132-179 (FastCameras._make_device_data: float32 [n,3,3] = lower
+ * left, horizontal, vertical, plus static origin/u/v and the float64 lens radius).
+ * The host side packs the numbers (bit-equal to the reference's NumPy arithmetic); these
+ * calls only move them. h_world / h_cam_dyn may be NULL to leave that part unchanged.
+ * ----------------------------------------------------------------------------------- */
+int rf_set_world(rf_ctx *ctx, int n, const float *h_world, void *stream);
+int rf_set_cameras(rf_ctx *ctx, int n, const float *h_cam_dyn, const float origin[3],
+                   const float u[3], const float v[3], double lens_radius, void *stream);
+/* Number of envs of the last rf_set_world (reference render.py:174 sizes the batch by
+ * len(self._worlds)); 0 before any update. */
+int rf_scene_envs(const rf_ctx *ctx);
+
+/* -------------------------------------------------------------------------------------
+ * Tracer. Replaces the kernel launch of reference graphics/render.py:165-246
+ * (FastRenderer.render / FastRenderer._device_render) for the first `n` envs of the
+ * scene: spp samples per pixel, pixel (e, y, x) uses RNG state e*H*W + y*W + x and leaves
+ * it advanced. Outputs (either may be NULL, not both):
+ *   d_rgb  uint8 [n, H, W, 3]  exactly the reference's frames;
+ *   d_gray uint8 [n, H, W]     cv2.cvtColor(RGB2GRAY) of those frames, produced in
+ *                              registers without the RGB round trip.
+ * Requires rf_rng_ensure(n*H*W) (called internally with seed 0 if needed).
+ * ----------------------------------------------------------------------------------- */
+int rf_render(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint8_t *d_gray,
+              void *stream);
+
+/* -------------------------------------------------------------------------------------
+ * Focus measure. Replaces reference vision.py:11-39 (focus_value / focus_values:
+ * cv2.cvtColor -> cv2.medianBlur(3) -> cv2.Laplacian(CV_8U) -> ndarray.var()).
+ * d_img is uint8 [n, H, W, channels] with channels 1 (gray) or 3 (RGB);
+ * d_out float64 [n].
+ * ----------------------------------------------------------------------------------- */
+int rf_focus(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, int channels,
+             double *d_out, void *stream);
+/* Debug/parity variant that also writes the intermediate planes (uint8 [n, H, W] each,
+ * may be NULL). */
+int rf_focus_planes(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, int channels,
+                    double *d_out, uint8_t *d_median, uint8_t *d_laplacian, void *stream);
+
+/* -------------------------------------------------------------------------------------
+ * One hot-path step = what reference environments/state_observer.py:359-383
+ * (FocusObserver.observe) does per call: set targets/focus planes, render, focus values.
+ * Host buffers in, host focus values out; the H2D/D2H copies, both kernels and the final
+ * synchronisation are all inside the call ("synchronous"). Frames never leave the GPU.
+ *   h_world float32 [n,2], h_cam_dyn float32 [n,9] (as rf_set_world / rf_set_cameras),
+ *   h_focus float64 [n].
+ * rf_step_device is the same with the focus values left on the device (no sync).
+ * ----------------------------------------------------------------------------------- */
+int rf_step_host(rf_ctx *ctx, int n, int H, int spp, const float *h_world,
+                 const float *h_cam_dyn, double *h_focus, void *stream);
+int rf_step_device(rf_ctx *ctx, int n, int H, int spp, double *d_focus, void *stream);
+
+/* -------------------------------------------------------------------------------------
+ * Self-checks and measurement helpers (used by tests/ and bench.py).
+ * ----------------------------------------------------------------------------------- */
+/* Exhaustively compares the kernel's table-based checkerboard cell test against
+ * sin(32*pi*u) evaluated in float64 on the device for every float32 u in [0, 1];
+ * *mismatches receives the count (must be 0). */
+int rf_selftest_checker(rf_ctx *ctx, int64_t *mismatches, void *stream);
+/* Measures the FP32 FFMA peak of this GPU (dependent-chain-free FFMA loop on all SMs);
+ * returns TFLOP/s counting 2 flop per FFMA. */
+int rf_measure_fp32_peak(rf_ctx *ctx, double *tflops, double *sm_clock_mhz_seen);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,594 @@
+// C-ABI of the reinfocus_b200 hot path (include/reinfocus_b200.h). Host-side plumbing
+// only: context, buffers, launches. The kernels live in rf_rng.cuh / rf_tracer.cuh /
+// rf_focus.cuh. Built for sm_100a only (see reinfocus_b200/build.py).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/reinfocus_b200.h"
+#include "rf_focus.cuh"
+#include "rf_rng.cuh"
+#include "rf_tracer.cuh"
+
+#define RF_ABI_VERSION 1
+
+namespace {
+
+thread_local std::string g_global_error;
+
+}  // namespace
+
+struct rf_ctx {
+    int device = 0;
+    cudaDeviceProp prop{};
+    std::string error;
+    int64_t launches = 0;
+
+    // RNG
+    rf::RngState *states = nullptr;
+    int64_t n_states = 0;
+    rf::JumpMatrix *d_levels = nullptr;  // [kJumpLevels]
+
+    // scene
+    float *d_world = nullptr;    // [cap_envs, 2]
+    float *d_cam_dyn = nullptr;  // [cap_envs, 9]
+    int cap_world = 0, cap_cam = 0;
+    int n_world = 0, n_cam = 0;
+    float origin[3] = {0, 0, 0}, u[3] = {1, 0, 0}, v[3] = {0, 1, 0};
+    double lens_radius = 0.05;
+    bool have_world = false, have_cam = false;
+
+    // focus scratch
+    unsigned long long *d_accum = nullptr;  // [cap_focus, 2]
+    unsigned int *d_tickets = nullptr;      // [cap_focus]
+    int cap_focus = 0;
+
+    // step scratch
+    uint8_t *d_gray = nullptr;
+    int64_t cap_gray = 0;
+    double *d_focus = nullptr;
+    int cap_focus_out = 0;
+    unsigned long long *d_misc = nullptr;  // small scratch (selftests)
+};
+
+namespace {
+
+int fail(rf_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    g_global_error = buf;
+    return code;
+}
+
+#define RF_CUDA(ctx, call)                                                              \
+    do {                                                                                \
+        cudaError_t err__ = (call);                                                     \
+        if (err__ != cudaSuccess)                                                       \
+            return fail((ctx), err__ == cudaErrorMemoryAllocation ? RF_ERR_NOMEM : RF_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, \
+                        __LINE__);                                                      \
+    } while (0)
+
+#define RF_REQUIRE(ctx, cond, ...)                                    \
+    do {                                                              \
+        if (!(cond)) return fail((ctx), RF_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        cudaGetDevice(&prev);
+        if (prev != device) cudaSetDevice(device);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// bit k set: u = k/32 maps to x = fl64(fl64(32 pi) * k/32) < k*pi (see rf_tracer.cuh).
+// long double (x87, 64-bit mantissa) separates x from k*pi unless they are closer than
+// ~1e-17 relative, which is asserted not to happen.
+int checker_below_mask(uint64_t *mask_out) {
+    const double c = 32.0 * 3.14159265358979323846;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    uint64_t mask = 0;
+    for (int k = 1; k <= 32; ++k) {
+        const float u = (float)k / 32.0f;
+        const double x = c * (double)u;
+        const long double d = (long double)x - (long double)k * pi;
+        if (fabsl(d) < 1e-15L * (long double)k) return -1;  // undecidable: never happens
+        if (d < 0) mask |= (1ull << k);
+    }
+    *mask_out = mask;
+    return 0;
+}
+
+int grow(rf_ctx *ctx, void **ptr, size_t bytes) {
+    if (*ptr) {
+        RF_CUDA(ctx, cudaFree(*ptr));
+        *ptr = nullptr;
+    }
+    RF_CUDA(ctx, cudaMalloc(ptr, bytes));
+    return RF_OK;
+}
+
+int ensure_focus_scratch(rf_ctx *ctx, int n, cudaStream_t stream) {
+    if (n <= ctx->cap_focus) return RF_OK;
+    const int cap = std::max(n, 64);
+    if (int rc = grow(ctx, (void **)&ctx->d_accum, sizeof(unsigned long long) * 2 * cap)) return rc;
+    if (int rc = grow(ctx, (void **)&ctx->d_tickets, sizeof(unsigned int) * cap)) return rc;
+    RF_CUDA(ctx, cudaMemsetAsync(ctx->d_accum, 0, sizeof(unsigned long long) * 2 * cap, stream));
+    RF_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, sizeof(unsigned int) * cap, stream));
+    ctx->cap_focus = cap;
+    return RF_OK;
+}
+
+int rng_init_into(rf_ctx *ctx, rf::RngState *d_states, int64_t n, uint64_t seed,
+                  cudaStream_t stream) {
+    if (n <= 0) return RF_OK;
+    const rf::RngState first = rf::rng_seed_state(seed);
+    RF_CUDA(ctx, cudaMemcpyAsync(d_states, &first, sizeof(first), cudaMemcpyHostToDevice, stream));
+    // the host buffer is on the stack: make sure the copy has consumed it
+    RF_CUDA(ctx, cudaStreamSynchronize(stream));
+    int level = 0;
+    for (int64_t filled = 1; filled < n; filled *= 2, ++level) {
+        if (level >= rf::kJumpLevels) return fail(ctx, RF_ERR_INVALID, "too many RNG states");
+        const int64_t count = std::min(filled, n - filled);
+        const int64_t blocks = (count + 255) / 256;
+        rf::rng_double_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_states, ctx->d_levels + level,
+                                                                   filled, count);
+        ctx->launches++;
+    }
+    RF_CUDA(ctx, cudaGetLastError());
+    return RF_OK;
+}
+
+int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint8_t *d_gray,
+                 cudaStream_t stream) {
+    rf::TraceParams p{};
+    p.world = ctx->d_world;
+    p.cam_dyn = ctx->d_cam_dyn;
+    p.states = ctx->states;
+    p.rgb = d_rgb;
+    p.gray = d_gray;
+    for (int i = 0; i < 3; ++i) {
+        p.origin[i] = ctx->origin[i];
+        p.u[i] = ctx->u[i];
+        p.v[i] = ctx->v[i];
+    }
+    p.lens_radius = ctx->lens_radius;
+    p.scale = (float)(255.0 / (double)spp);
+    p.n = n;
+    p.H = H;
+    p.W = W;
+    p.spp = spp;
+    p.total = (int64_t)n * H * W;
+    const int64_t blocks = (p.total + rf::kTraceThreads - 1) / rf::kTraceThreads;
+    if (blocks > 0x7fffffffLL) return fail(ctx, RF_ERR_INVALID, "render batch too large");
+    rf::trace_kernel<<<(unsigned)blocks, rf::kTraceThreads, 0, stream>>>(p);
+    ctx->launches++;
+    RF_CUDA(ctx, cudaGetLastError());
+    return RF_OK;
+}
+
+int launch_focus(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, int channels,
+                 double *d_out, uint8_t *d_median, uint8_t *d_laplacian, cudaStream_t stream) {
+    if (int rc = ensure_focus_scratch(ctx, n, stream)) return rc;
+    rf::FocusParams p{};
+    p.img = d_img;
+    p.out = d_out;
+    p.median = d_median;
+    p.laplacian = d_laplacian;
+    p.accum = ctx->d_accum;
+    p.tickets = ctx->d_tickets;
+    p.n = n;
+    p.H = H;
+    p.W = W;
+    p.channels = channels;
+    p.pitch = (W + 3) & ~3;
+    // rows per block: fill the GPU (>= 2 blocks per SM when the batch is small) but keep
+    // the +-2 row halo overhead low; bounded by shared memory
+    const int sms = ctx->prop.multiProcessorCount;
+    int rows = 32;
+    while (rows > 4 && (int64_t)n * ((H + rows - 1) / rows) < 2LL * sms) rows /= 2;
+    const size_t max_smem = 200 * 1024;
+    while (rows > 1 && (size_t)(2 * rows + 6) * p.pitch > max_smem) rows /= 2;
+    const size_t smem = (size_t)(2 * rows + 6) * p.pitch;
+    if (smem > max_smem) return fail(ctx, RF_ERR_INVALID, "image too wide for the focus kernel");
+    p.rows = rows;
+    if (smem > 48 * 1024)
+        RF_CUDA(ctx, cudaFuncSetAttribute(rf::focus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+    const dim3 grid((H + rows - 1) / rows, n);
+    if (n > 65535) {
+        // gridDim.y limit: split the batch
+        for (int first = 0; first < n; first += 65535) {
+            const int cnt = std::min(65535, n - first);
+            rf::FocusParams q = p;
+            q.img = d_img + (int64_t)first * H * W * channels;
+            q.out = d_out + first;
+            q.median = d_median ? d_median + (int64_t)first * H * W : nullptr;
+            q.laplacian = d_laplacian ? d_laplacian + (int64_t)first * H * W : nullptr;
+            q.accum = ctx->d_accum + 2 * (int64_t)first;
+            q.tickets = ctx->d_tickets + first;
+            q.n = cnt;
+            rf::focus_kernel<<<dim3(grid.x, cnt), rf::kFocusThreads, smem, stream>>>(q);
+            ctx->launches++;
+        }
+    } else {
+        rf::focus_kernel<<<grid, rf::kFocusThreads, smem, stream>>>(p);
+        ctx->launches++;
+    }
+    RF_CUDA(ctx, cudaGetLastError());
+    return RF_OK;
+}
+
+__global__ void ffma_peak_kernel(float *out, int iters) {
+    // 8 independent FFMA chains per thread: enough ILP to saturate both FMA pipes
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace
+
+extern "C" {
+
+int rf_abi_version(void) { return RF_ABI_VERSION; }
+
+const char *rf_last_global_error(void) { return g_global_error.c_str(); }
+
+const char *rf_last_error(const rf_ctx *ctx) { return ctx ? ctx->error.c_str() : g_global_error.c_str(); }
+
+int rf_create(rf_ctx **out, int device) {
+    if (!out) return fail(nullptr, RF_ERR_INVALID, "rf_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    RF_CUDA(nullptr, cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count)
+        return fail(nullptr, RF_ERR_INVALID, "rf_create: device %d out of range (%d visible)", device, count);
+    rf_ctx *ctx = new rf_ctx();
+    ctx->device = device;
+    DeviceGuard guard(device);
+    cudaError_t err = cudaGetDeviceProperties(&ctx->prop, device);
+    if (err != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, RF_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(err));
+    }
+    if (ctx->prop.major != 10) {
+        const int major = ctx->prop.major, minor = ctx->prop.minor;
+        delete ctx;
+        return fail(nullptr, RF_ERR_CUDA,
+                    "reinfocus_b200 is built for sm_100a only; device %d is sm_%d%d", device, major, minor);
+    }
+    std::vector<rf::JumpMatrix> levels(rf::kJumpLevels);
+    rf::build_jump_levels(levels.data());
+    uint64_t mask = 0;
+    if (checker_below_mask(&mask) != 0) {
+        delete ctx;
+        return fail(nullptr, RF_ERR_INVALID, "checker boundary table is undecidable");
+    }
+    auto cleanup = [&](int code) {
+        rf_destroy(ctx);
+        return code;
+    };
+    if (cudaMalloc((void **)&ctx->d_levels, sizeof(rf::JumpMatrix) * rf::kJumpLevels) != cudaSuccess)
+        return cleanup(fail(nullptr, RF_ERR_NOMEM, "cudaMalloc(jump levels) failed"));
+    if (cudaMemcpy(ctx->d_levels, levels.data(), sizeof(rf::JumpMatrix) * rf::kJumpLevels,
+                   cudaMemcpyHostToDevice) != cudaSuccess)
+        return cleanup(fail(nullptr, RF_ERR_CUDA, "cudaMemcpy(jump levels) failed"));
+    if (cudaMemcpyToSymbol(rf::c_checker_below_mask, &mask, sizeof(mask)) != cudaSuccess)
+        return cleanup(fail(nullptr, RF_ERR_CUDA, "cudaMemcpyToSymbol(checker mask) failed"));
+    if (cudaMalloc((void **)&ctx->d_misc, 64) != cudaSuccess)
+        return cleanup(fail(nullptr, RF_ERR_NOMEM, "cudaMalloc(misc) failed"));
+    *out = ctx;
+    return RF_OK;
+}
+
+int rf_destroy(rf_ctx *ctx) {
+    if (!ctx) return RF_OK;
+    DeviceGuard guard(ctx->device);
+    cudaFree(ctx->states);
+    cudaFree(ctx->d_levels);
+    cudaFree(ctx->d_world);
+    cudaFree(ctx->d_cam_dyn);
+    cudaFree(ctx->d_accum);
+    cudaFree(ctx->d_tickets);
+    cudaFree(ctx->d_gray);
+    cudaFree(ctx->d_focus);
+    cudaFree(ctx->d_misc);
+    delete ctx;
+    return RF_OK;
+}
+
+int rf_device_info(const rf_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, int *clock_khz) {
+    if (!ctx) return fail(nullptr, RF_ERR_INVALID, "rf_device_info: ctx is NULL");
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = ctx->prop.major;
+    if (cc_minor) *cc_minor = ctx->prop.minor;
+    if (clock_khz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        *clock_khz = khz;
+    }
+    return RF_OK;
+}
+
+int64_t rf_launch_count(const rf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------- RNG
+
+int rf_rng_ensure(rf_ctx *ctx, int64_t n_states, uint64_t seed, void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_rng_ensure: ctx is NULL");
+    RF_REQUIRE(ctx, n_states >= 0, "rf_rng_ensure: negative n_states");
+    if (ctx->states && ctx->n_states >= n_states) return RF_OK;
+    DeviceGuard guard(ctx->device);
+    if (ctx->states) {
+        // frees are stream-agnostic: make sure no kernel still reads the old buffer
+        RF_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+        RF_CUDA(ctx, cudaFree(ctx->states));
+        ctx->states = nullptr;
+        ctx->n_states = 0;
+    }
+    if (n_states == 0) return RF_OK;
+    RF_CUDA(ctx, cudaMalloc((void **)&ctx->states, sizeof(rf::RngState) * (size_t)n_states));
+    ctx->n_states = n_states;
+    return rng_init_into(ctx, ctx->states, n_states, seed, (cudaStream_t)stream);
+}
+
+int rf_rng_reset(rf_ctx *ctx) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_rng_reset: ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    if (ctx->states) {
+        RF_CUDA(ctx, cudaDeviceSynchronize());
+        RF_CUDA(ctx, cudaFree(ctx->states));
+    }
+    ctx->states = nullptr;
+    ctx->n_states = 0;
+    return RF_OK;
+}
+
+int64_t rf_rng_count(const rf_ctx *ctx) { return ctx ? ctx->n_states : 0; }
+
+int rf_rng_export(rf_ctx *ctx, rf_rng_state *h_dst, int64_t first, int64_t n) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_rng_export: ctx is NULL");
+    RF_REQUIRE(ctx, first >= 0 && n >= 0 && first + n <= ctx->n_states,
+               "rf_rng_export: range [%lld, %lld) outside %lld states", (long long)first,
+               (long long)(first + n), (long long)ctx->n_states);
+    DeviceGuard guard(ctx->device);
+    RF_CUDA(ctx, cudaDeviceSynchronize());
+    RF_CUDA(ctx, cudaMemcpy(h_dst, ctx->states + first, sizeof(rf::RngState) * (size_t)n,
+                            cudaMemcpyDeviceToHost));
+    return RF_OK;
+}
+
+int rf_rng_import(rf_ctx *ctx, const rf_rng_state *h_src, int64_t first, int64_t n) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_rng_import: ctx is NULL");
+    RF_REQUIRE(ctx, first >= 0 && n >= 0 && first + n <= ctx->n_states,
+               "rf_rng_import: range [%lld, %lld) outside %lld states", (long long)first,
+               (long long)(first + n), (long long)ctx->n_states);
+    DeviceGuard guard(ctx->device);
+    RF_CUDA(ctx, cudaDeviceSynchronize());
+    RF_CUDA(ctx, cudaMemcpy(ctx->states + first, h_src, sizeof(rf::RngState) * (size_t)n,
+                            cudaMemcpyHostToDevice));
+    return RF_OK;
+}
+
+int rf_rng_init_device(rf_ctx *ctx, rf_rng_state *d_states, int64_t n, uint64_t seed, void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_rng_init_device: ctx is NULL");
+    RF_REQUIRE(ctx, n >= 0 && (n == 0 || d_states), "rf_rng_init_device: bad buffer");
+    DeviceGuard guard(ctx->device);
+    return rng_init_into(ctx, reinterpret_cast<rf::RngState *>(d_states), n, seed, (cudaStream_t)stream);
+}
+
+int rf_rng_uniform_device(rf_ctx *ctx, rf_rng_state *d_states, int64_t n, int draws, float *d_out,
+                          void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_rng_uniform_device: ctx is NULL");
+    RF_REQUIRE(ctx, n >= 0 && draws >= 0, "rf_rng_uniform_device: negative size");
+    if (n == 0 || draws == 0) return RF_OK;
+    DeviceGuard guard(ctx->device);
+    rf::rng_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<rf::RngState *>(d_states), n, draws, d_out);
+    ctx->launches++;
+    RF_CUDA(ctx, cudaGetLastError());
+    return RF_OK;
+}
+
+// -------------------------------------------------------------------------------- scene
+
+int rf_set_world(rf_ctx *ctx, int n, const float *h_world, void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_set_world: ctx is NULL");
+    RF_REQUIRE(ctx, n > 0 && h_world, "rf_set_world: empty world");
+    DeviceGuard guard(ctx->device);
+    if (n > ctx->cap_world) {
+        RF_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+        if (int rc = grow(ctx, (void **)&ctx->d_world, sizeof(float) * 2 * (size_t)n)) return rc;
+        ctx->cap_world = n;
+    }
+    RF_CUDA(ctx, cudaMemcpyAsync(ctx->d_world, h_world, sizeof(float) * 2 * (size_t)n,
+                                 cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    ctx->n_world = n;
+    ctx->have_world = true;
+    return RF_OK;
+}
+
+int rf_set_cameras(rf_ctx *ctx, int n, const float *h_cam_dyn, const float origin[3], const float u[3],
+                   const float v[3], double lens_radius, void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_set_cameras: ctx is NULL");
+    RF_REQUIRE(ctx, n > 0 && h_cam_dyn, "rf_set_cameras: empty cameras");
+    RF_REQUIRE(ctx, origin && u && v, "rf_set_cameras: static camera vectors are NULL");
+    DeviceGuard guard(ctx->device);
+    if (n > ctx->cap_cam) {
+        RF_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+        if (int rc = grow(ctx, (void **)&ctx->d_cam_dyn, sizeof(float) * 9 * (size_t)n)) return rc;
+        ctx->cap_cam = n;
+    }
+    RF_CUDA(ctx, cudaMemcpyAsync(ctx->d_cam_dyn, h_cam_dyn, sizeof(float) * 9 * (size_t)n,
+                                 cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    for (int i = 0; i < 3; ++i) {
+        ctx->origin[i] = origin[i];
+        ctx->u[i] = u[i];
+        ctx->v[i] = v[i];
+    }
+    ctx->lens_radius = lens_radius;
+    ctx->n_cam = n;
+    ctx->have_cam = true;
+    return RF_OK;
+}
+
+int rf_scene_envs(const rf_ctx *ctx) { return ctx && ctx->have_world ? ctx->n_world : 0; }
+
+// ------------------------------------------------------------------------------- render
+
+static int check_render_args(rf_ctx *ctx, const char *who, int n, int H, int W, int spp) {
+    RF_REQUIRE(ctx, ctx != nullptr, "%s: ctx is NULL", who);
+    if (!ctx->have_world || !ctx->have_cam)
+        return fail(ctx, RF_ERR_NO_SCENE, "%s: targets and focus planes must be set before rendering", who);
+    RF_REQUIRE(ctx, n > 0 && H > 0 && W > 0 && spp > 0, "%s: n, H, W, spp must be positive", who);
+    RF_REQUIRE(ctx, n <= ctx->n_world, "%s: %d envs requested but the world holds %d", who, n, ctx->n_world);
+    RF_REQUIRE(ctx, n <= ctx->n_cam, "%s: %d envs requested but only %d cameras are set", who, n, ctx->n_cam);
+    return RF_OK;
+}
+
+int rf_render(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint8_t *d_gray, void *stream) {
+    if (int rc = check_render_args(ctx, "rf_render", n, H, W, spp)) return rc;
+    RF_REQUIRE(ctx, d_rgb || d_gray, "rf_render: no output buffer");
+    DeviceGuard guard(ctx->device);
+    if (int rc = rf_rng_ensure(ctx, (int64_t)n * H * W, 0, stream)) return rc;
+    return launch_trace(ctx, n, H, W, spp, d_rgb, d_gray, (cudaStream_t)stream);
+}
+
+// -------------------------------------------------------------------------------- focus
+
+int rf_focus_planes(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, int channels, double *d_out,
+                    uint8_t *d_median, uint8_t *d_laplacian, void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_focus: ctx is NULL");
+    RF_REQUIRE(ctx, n >= 0 && H > 0 && W > 0, "rf_focus: bad image shape");
+    RF_REQUIRE(ctx, channels == 1 || channels == 3, "rf_focus: channels must be 1 or 3");
+    if (n == 0) return RF_OK;
+    RF_REQUIRE(ctx, d_img && d_out, "rf_focus: NULL buffer");
+    DeviceGuard guard(ctx->device);
+    return launch_focus(ctx, n, H, W, d_img, channels, d_out, d_median, d_laplacian, (cudaStream_t)stream);
+}
+
+int rf_focus(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, int channels, double *d_out,
+             void *stream) {
+    return rf_focus_planes(ctx, n, H, W, d_img, channels, d_out, nullptr, nullptr, stream);
+}
+
+// --------------------------------------------------------------------------------- step
+
+static int ensure_step_scratch(rf_ctx *ctx, int n, int H, cudaStream_t stream) {
+    const int64_t need = (int64_t)n * H * H;
+    if (need > ctx->cap_gray) {
+        RF_CUDA(ctx, cudaStreamSynchronize(stream));
+        if (int rc = grow(ctx, (void **)&ctx->d_gray, (size_t)need)) return rc;
+        ctx->cap_gray = need;
+    }
+    if (n > ctx->cap_focus_out) {
+        RF_CUDA(ctx, cudaStreamSynchronize(stream));
+        if (int rc = grow(ctx, (void **)&ctx->d_focus, sizeof(double) * (size_t)n)) return rc;
+        ctx->cap_focus_out = n;
+    }
+    return RF_OK;
+}
+
+int rf_step_device(rf_ctx *ctx, int n, int H, int spp, double *d_focus, void *stream) {
+    if (int rc = check_render_args(ctx, "rf_step_device", n, H, H, spp)) return rc;
+    RF_REQUIRE(ctx, d_focus, "rf_step_device: d_focus is NULL");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int rc = ensure_step_scratch(ctx, n, H, s)) return rc;
+    if (int rc = rf_rng_ensure(ctx, (int64_t)n * H * H, 0, stream)) return rc;
+    if (int rc = launch_trace(ctx, n, H, H, spp, nullptr, ctx->d_gray, s)) return rc;
+    return launch_focus(ctx, n, H, H, ctx->d_gray, 1, d_focus, nullptr, nullptr, s);
+}
+
+int rf_step_host(rf_ctx *ctx, int n, int H, int spp, const float *h_world, const float *h_cam_dyn,
+                 double *h_focus, void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_step_host: ctx is NULL");
+    RF_REQUIRE(ctx, h_focus, "rf_step_host: h_focus is NULL");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h_world)
+        if (int rc = rf_set_world(ctx, n, h_world, stream)) return rc;
+    if (h_cam_dyn)
+        if (int rc = rf_set_cameras(ctx, n, h_cam_dyn, ctx->origin, ctx->u, ctx->v, ctx->lens_radius, stream))
+            return rc;
+    if (int rc = check_render_args(ctx, "rf_step_host", n, H, H, spp)) return rc;
+    if (int rc = ensure_step_scratch(ctx, n, H, s)) return rc;
+    if (int rc = rf_step_device(ctx, n, H, spp, ctx->d_focus, stream)) return rc;
+    RF_CUDA(ctx, cudaMemcpyAsync(h_focus, ctx->d_focus, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    RF_CUDA(ctx, cudaStreamSynchronize(s));
+    return RF_OK;
+}
+
+// ---------------------------------------------------------------------------- self-checks
+
+int rf_selftest_checker(rf_ctx *ctx, int64_t *mismatches, void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr && mismatches, "rf_selftest_checker: NULL argument");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    RF_CUDA(ctx, cudaMemsetAsync(ctx->d_misc, 0, sizeof(unsigned long long), s));
+    rf::checker_selftest_kernel<<<ctx->prop.multiProcessorCount * 8, 256, 0, s>>>(ctx->d_misc);
+    ctx->launches++;
+    RF_CUDA(ctx, cudaGetLastError());
+    unsigned long long bad = 0;
+    RF_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->d_misc, sizeof(bad), cudaMemcpyDeviceToHost, s));
+    RF_CUDA(ctx, cudaStreamSynchronize(s));
+    *mismatches = (int64_t)bad;
+    return RF_OK;
+}
+
+int rf_measure_fp32_peak(rf_ctx *ctx, double *tflops, double *sm_clock_mhz_seen) {
+    RF_REQUIRE(ctx, ctx != nullptr && tflops, "rf_measure_fp32_peak: NULL argument");
+    DeviceGuard guard(ctx->device);
+    const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float *d_out = nullptr;
+    RF_CUDA(ctx, cudaMalloc((void **)&d_out, sizeof(float) * blocks * threads));
+    cudaEvent_t e0, e1;
+    RF_CUDA(ctx, cudaEventCreate(&e0));
+    RF_CUDA(ctx, cudaEventCreate(&e1));
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 6; ++rep) {
+        RF_CUDA(ctx, cudaEventRecord(e0, 0));
+        ffma_peak_kernel<<<blocks, threads>>>(d_out, iters);
+        ctx->launches++;
+        RF_CUDA(ctx, cudaEventRecord(e1, 0));
+        RF_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        RF_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best_ms = std::min(best_ms, (double)ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    const double flop = 2.0 * 64.0 * iters * (double)blocks * threads;
+    *tflops = flop / (best_ms * 1e-3) / 1e12;
+    if (sm_clock_mhz_seen) {
+        // FFMA issue rate -> implied clock: 128 lanes/SM/clk
+        *sm_clock_mhz_seen = (*tflops * 1e12 / 2.0) / (128.0 * ctx->prop.multiProcessorCount) / 1e6;
+    }
+    return RF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+"""Pins the CPU oracle (oracle/rf_oracle.c) against golden vectors produced by the
+unmodified reference (oracle/gen_golden_sim.py): the reference's graphics run under
+numba's CUDA simulator ("SIM profile"), numba's own RNG initialiser/sampler, and
+cv2-backed reinfocus.vision. Everything here is bit-exact."""
+
+import glob
+import os
+
+import numpy
+import pytest
+
+import oracle
+
+
+def _load(golden_dir, name):
+    return numpy.load(os.path.join(golden_dir, name))
+
+
+# --------------------------------------------------------------------------- RNG (a3, a6)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 12345, 2**63 + 5])
+def test_rng_states_match_numba(golden_dir, seed):
+    gold = _load(golden_dir, "rng_numba.npz")
+    states = oracle.rng_states(3000, seed)
+    got = numpy.stack([states["s0"], states["s1"]], axis=1)
+    # the golden states were sampled 16 times on the first 8 generators afterwards
+    numpy.testing.assert_array_equal(got[8:], gold[f"states_seed{seed}"][8:])
+    draws = numpy.array([[oracle.uniform_float32(states, i) for _ in range(16)] for i in range(8)],
+                        dtype=numpy.float32)
+    numpy.testing.assert_array_equal(draws, gold[f"uniform_seed{seed}"])
+    after = numpy.stack([states["s0"][:8], states["s1"][:8]], axis=1)
+    numpy.testing.assert_array_equal(after, gold[f"after_seed{seed}"])
+
+
+def test_rng_known_answers_from_survey():
+    # numba 0.65.0, seed 0
+    s = oracle.rng_states(5, 0)
+    assert (int(s["s0"][0]), int(s["s1"][0])) == (0xE220A8397B1DCDAF, 0xE220A8397B1DCDAF)
+    assert (int(s["s0"][1]), int(s["s1"][1])) == (0x12513CE25BE05EB1, 0x70D189C276BA17A4)
+    assert (int(s["s0"][4]), int(s["s1"][4])) == (0xF3F7977FBDB707D4, 0x835F7E5B8340C6CA)
+    draws = [float(oracle.uniform_float32(s, 0)) for _ in range(4)]
+    assert draws == [0.7666215896606445, 0.8435220718383789, 0.6734751462936401,
+                     0.6150838732719421]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 1000, 4097])
+def test_rng_doubling_equals_chain(n):
+    chain = oracle.rng_states(n, 7)
+    doubled = oracle.rng_states(n, 7, doubling=True)
+    numpy.testing.assert_array_equal(chain, doubled)
+
+
+# ------------------------------------------------------------- tracer, SIM profile (a1-a11)
+
+
+def _render_cases(golden_dir):
+    return sorted(glob.glob(os.path.join(golden_dir, "sim_render_*.npz")))
+
+
+@pytest.mark.parametrize("path", _render_cases(os.path.join(os.path.dirname(__file__), "golden")),
+                         ids=lambda p: os.path.basename(p)[11:-4])
+def test_sim_profile_reproduces_reference_under_cudasim(path):
+    gold = numpy.load(path)
+    renderer = oracle.OracleFastRenderer(samples_per_pixel=int(gold["spp"]),
+                                         r_size=float(gold["r_size"]),
+                                         profile=oracle.PROFILE_SIM)
+    for i in range(int(gold["n_calls"])):
+        renderer.update_targets(gold[f"targets_{i}"])
+        renderer.update_focus_planes(gold[f"planes_{i}"])
+        # host-side packing (reference world.py:100-123, camera.py:132-179)
+        numpy.testing.assert_array_equal(renderer.world, gold[f"world_{i}"])
+        numpy.testing.assert_array_equal(renderer.cam, gold[f"cam_dyn_{i}"])
+        st = renderer.statics
+        numpy.testing.assert_array_equal(
+            numpy.array([*st.look_from, *st.u, *st.v], dtype=numpy.float32), gold[f"cam_static_{i}"])
+        assert float(st.half_aperture) == float(gold[f"lens_{i}"])
+        frames = renderer.render(int(gold[f"height_{i}"]))
+        assert len(renderer.states) == int(gold[f"n_states_{i}"])
+        numpy.testing.assert_array_equal(frames, gold[f"frames_{i}"])
+        # the oracle's variance is the exactly rounded rational (N*S2 - S^2)/N^2; numpy's
+        # var() accumulates float64 squares pairwise and may sit an ulp or two off it
+        numpy.testing.assert_allclose(oracle.focus_values(frames), gold[f"focus_{i}"], rtol=1e-14)
+
+
+def test_gpu_profile_differs_only_slightly_from_sim_profile():
+    """The two typings of the same algorithm: same draws, a handful of 1-level flips."""
+
+    frames = {}
+    for profile in (oracle.PROFILE_SIM, oracle.PROFILE_GPU):
+        r = oracle.OracleFastRenderer(samples_per_pixel=16, profile=profile)
+        r.update_targets([7.5, 6.0])
+        r.update_focus_planes([7.5, 9.0])
+        frames[profile] = r.render(64).astype(numpy.int16)
+    diff = numpy.abs(frames[oracle.PROFILE_SIM] - frames[oracle.PROFILE_GPU])
+    assert diff.max() <= 16  # one sample's worth at spp=16 (255/16)
+    assert (diff > 0).mean() < 2e-3
+
+
+# ---------------------------------------------------------------------- focus measure (a12)
+
+
+def test_focus_small_images_match_cv2(golden_dir):
+    gold = _load(golden_dir, "focus_cv2.npz")
+    for name in gold["small_names"]:
+        img = gold[f"img_{name}"]
+        got = oracle.focus_values(img[None])[0]
+        want = float(gold[f"fv_{name}"])
+        assert got == pytest.approx(want, rel=1e-13, abs=1e-13), name
+    # reference tests/vision_test.py:14-34 and SURVEY.md known answer
+    assert oracle.focus_values(gold["img_zeros"][None])[0] == 0.0
+    assert oracle.focus_values(gold["img_ones"][None])[0] == 0.0
+    assert oracle.focus_values(gold["img_checker10"][None])[0] == pytest.approx(
+        16230.240000000005, rel=1e-14)
+
+
+def test_focus_large_images_match_cv2(golden_dir):
+    gold = _load(golden_dir, "focus_cv2.npz")
+    for (h, w, seed), want in zip(gold["large_specs"], gold["large_fv"]):
+        g = numpy.random.Generator(numpy.random.PCG64(int(seed)))
+        base = numpy.linspace(0, 200, w)[None, :, None] + g.integers(0, 40, size=(h, w, 3))
+        img = base.astype(numpy.uint8)
+        got = oracle.focus_values(img[None])[0]
+        assert got == pytest.approx(float(want), rel=1e-13)
+
+
+def test_focus_batch_matches_cv2(golden_dir):
+    gold = _load(golden_dir, "focus_cv2.npz")
+    got = oracle.focus_values(gold["batch_imgs"])
+    numpy.testing.assert_allclose(got, gold["batch_fv"], rtol=1e-13)
+
+
+def test_focus_against_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = numpy.random.default_rng(5)
+    for shape in [(5, 5), (12, 31), (64, 64), (100, 75)]:
+        img = rng.integers(0, 256, size=shape + (3,), dtype=numpy.uint8)
+        gray = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)
+        numpy.testing.assert_array_equal(oracle.gray(img), gray)
+        med = cv2.medianBlur(gray, 3)
+        lap = cv2.Laplacian(med, cv2.CV_8U)
+        fv, omed, olap = oracle.focus_values_gray(gray, planes=True)
+        numpy.testing.assert_array_equal(omed[0], med)
+        numpy.testing.assert_array_equal(olap[0], lap)
+        assert fv[0] == pytest.approx(lap.var(), rel=1e-13)
