@@ -1,0 +1,326 @@
+"""Benchmark of the reinfocus hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs 4096] [--impl ours|reference]
+
+One "step" = one FocusObserver.observe over the whole vector env: set targets / focus
+planes, ray trace every env's 300 x 300 frame at 100 samples per pixel, reduce each frame
+to its focus value. Metric: env-steps/s (BASELINE.json), whole job over all N GPUs, 4096
+envs in total (strong scaling: each rank owns 4096/N envs).
+
+`value`   : device-resident loop (scene already in HBM), CUDA-event timed, max over ranks.
+`e2e`     : the public API (FastRenderer.step_focus) with host buffers: host->device copy of
+            the step's parameters and device->host read of its focus values every step.
+`roofline`: the tracer kernel (dominant) against the FP32 FFMA peak measured live.
+`cpu_baseline` / `--impl reference`: the CPU oracle (C restatement of the reference, all
+            host cores) on a bounded sample of the same workload.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "env-steps/sec (render+focus value) at 4096 envs"
+UNIT = "env-steps/s"
+HEIGHT = 300
+SPP = 100
+FLOP_PER_RAY = 120.0
+THEORETICAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def synthetic_inputs(num_envs, steps, seed=1234):
+    """targets / focus planes ~ U[5, 10] float32 from PCG64DXSM(1234)."""
+
+    import numpy
+
+    rng = numpy.random.Generator(numpy.random.PCG64DXSM(seed))
+    targets = rng.uniform(5, 10, (steps, num_envs)).astype(numpy.float32)
+    planes = rng.uniform(5, 10, (steps, num_envs)).astype(numpy.float32)
+    return targets, planes
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                     "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                fields = [f.strip() for f in out.strip().split(",")]
+                if len(fields) >= 7:
+                    self.samples.append(fields)
+            except Exception:  # pylint: disable=broad-except
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=5)
+
+    def summary(self):
+        import statistics
+
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        smax = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def cpu_baseline(steps, warmup, cores_hint=None):
+    """The CPU oracle (oracle/, C restatement of the reference's numba kernel + cv2 focus
+    measure) on a bounded sample of the workload, all host threads."""
+
+    import numpy
+
+    import oracle
+
+    cores = oracle.max_threads()
+    sample_envs = int(min(512, max(16, 8 * cores)))
+    targets, planes = synthetic_inputs(sample_envs, steps + warmup)
+    states = oracle.rng_states(sample_envs * HEIGHT * HEIGHT, 0, doubling=True)
+    times = []
+    for i in range(steps + warmup):
+        t0 = time.perf_counter()
+        world = oracle.pack_world(targets[i])
+        cam = oracle.pack_cameras(planes[i])
+        oracle.step(world, cam, HEIGHT, SPP, states, profile=oracle.PROFILE_GPU)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    mean = float(numpy.mean(times))
+    return {
+        "value": sample_envs / mean, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{sample_envs} envs x {HEIGHT}x{HEIGHT} x {SPP} spp per step "
+                  f"({sample_envs * HEIGHT * HEIGHT * SPP:.3g} rays), {steps} timed steps",
+        "ms_per_step": mean * 1e3,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (the reference itself is
+    numba-CUDA only; its CPU statement is the oracle port, kind "port")."""
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_baseline(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32+f64+u64", "data": "synthetic",
+        "config": {"workload": f"DiscreteSteps-v0 hot path, {args.envs} envs, {HEIGHT}x{HEIGHT}, "
+                               f"{SPP} spp (CPU arm: bounded sample)"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy
+    import torch
+    import torch.distributed as dist
+
+    from reinfocus_b200 import parallel
+    from reinfocus_b200.graphics import render
+
+    rank, world_size, local_rank = parallel.init_from_env()
+    assert world_size == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world_size}"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+
+    first, last = parallel.shard_bounds(args.envs, world_size, rank)
+    n_local = last - first
+    total_steps = args.steps + args.warmup
+    targets, planes = synthetic_inputs(args.envs, 2 * total_steps)
+    targets, planes = targets[:, first:last], planes[:, first:last]
+
+    renderer = render.FastRenderer(samples_per_pixel=SPP, device=local_rank)
+    ctx = renderer.context
+    info = ctx.device_info()
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(value):
+        if world_size == 1:
+            return value
+        t = torch.tensor([value], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # one-time setup outside any timed region: RNG states for every pixel of the shard
+    t_init0 = time.perf_counter()
+    ctx.rng_ensure(n_local * HEIGHT * HEIGHT, 0)
+    torch.cuda.synchronize()
+    rng_init_s = time.perf_counter() - t_init0
+
+    focus_dev = torch.empty((n_local,), dtype=torch.float64, device=device)
+    gray_dev = torch.empty((n_local, HEIGHT, HEIGHT), dtype=torch.uint8, device=device)
+
+    # ------------------------------------------------------------- value: device-resident
+    renderer.update_targets(targets[0])
+    renderer.update_focus_planes(planes[0])
+    renderer._sync_scene()
+    for _ in range(args.warmup):
+        ctx.step_device(n_local, HEIGHT, SPP, focus_dev.data_ptr())
+        parallel.gather_observations(focus_dev, args.envs)
+    launches_before = ctx.launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        start.record()
+        for _ in range(args.steps):
+            ctx.step_device(n_local, HEIGHT, SPP, focus_dev.data_ptr())
+            gathered = parallel.gather_observations(focus_dev, args.envs)
+        stop.record()
+        barrier()
+    device_ms = max_over_ranks(start.elapsed_time(stop)) / args.steps
+    launches = ctx.launch_count() - launches_before
+    checksum = float(gathered.sum().item())
+
+    # ------------------------------------------- per-kernel timing (tracer, focus stencil)
+    trace_ms, focus_ms = [], []
+    for _ in range(min(args.steps, 3)):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        ctx.render(n_local, HEIGHT, HEIGHT, SPP, None, gray_dev.data_ptr())
+        e1.record()
+        ctx.focus(n_local, HEIGHT, HEIGHT, gray_dev.data_ptr(), 1, focus_dev.data_ptr())
+        e2.record()
+        torch.cuda.synchronize()
+        trace_ms.append(e0.elapsed_time(e1))
+        focus_ms.append(e1.elapsed_time(e2))
+    trace_ms = float(numpy.mean(trace_ms))
+    focus_ms = float(numpy.mean(focus_ms))
+
+    # --------------------------------------------------- e2e: public API with host buffers
+    for i in range(args.warmup):
+        renderer.step_focus(targets[total_steps + i], planes[total_steps + i], HEIGHT)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        fv = renderer.step_focus(targets[total_steps + args.warmup + i],
+                                 planes[total_steps + args.warmup + i], HEIGHT)
+        if world_size > 1:
+            parallel.gather_observations(torch.from_numpy(fv).to(device), args.envs)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+
+    if rank != 0:
+        return
+
+    rays_local = n_local * HEIGHT * HEIGHT * SPP
+    fp32_peak, implied_mhz = ctx.measure_fp32_peak()
+    achieved_tflops = rays_local * FLOP_PER_RAY / (trace_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    focus_bytes = n_local * HEIGHT * HEIGHT + 8 * n_local
+    base = cpu_baseline(max(1, min(args.steps, 2)), 1) if not args.no_cpu_baseline else None
+
+    line = {
+        "metric": METRIC, "value": args.envs / (device_ms * 1e-3), "unit": UNIT,
+        "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": device_ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32+f64+u64", "data": "synthetic",
+        "config": {
+            "workload": f"DiscreteSteps-v0 hot path (FocusObserver.observe): {args.envs} envs "
+                        f"sharded over {world_size} GPU(s), {HEIGHT}x{HEIGHT}, {SPP} spp, "
+                        f"render + focus value",
+            "envs_per_gpu": n_local, "rays_per_step": args.envs * HEIGHT * HEIGHT * SPP,
+            "l2": "inputs larger than L2 (RNG states: 16 B/pixel = "
+                  f"{n_local * HEIGHT * HEIGHT * 16 / 1e9:.2f} GB per GPU, read+written every step)",
+            "parallelism": f"env-sharded x{world_size}, obs all-gather",
+        },
+        "rays_per_s": args.envs * HEIGHT * HEIGHT * SPP / (device_ms * 1e-3),
+        "e2e": {"value": args.envs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": n_local * (2 + 9) * 4, "d2h_bytes_per_step": n_local * 8},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": {
+            "kernel": "rf::trace_kernel", "bound": "fp32",
+            "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+            "frac": achieved_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+            "peak_source": f"FFMA loop measured live on this GPU (implies {implied_mhz:.0f} MHz); "
+                           f"theoretical 148 SM x 128 x 2 x 1.965 GHz = {THEORETICAL_FP32_TFLOPS:.1f}",
+            "algorithmic_flop_per_ray": FLOP_PER_RAY, "rays_per_launch": rays_local,
+            "launch_ms": trace_ms, "rays_per_s": rays_local / (trace_ms * 1e-3),
+        },
+        "roofline_focus": {
+            "kernel": "rf::focus_kernel", "bound": "hbm", "achieved": focus_bytes / (focus_ms * 1e-3) / 1e9,
+            "peak": hbm_peak, "unit": "GB/s",
+            "frac": focus_bytes / (focus_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+            "launch_ms": focus_ms, "algorithmic_bytes_per_launch": focus_bytes,
+        },
+        "rng_init_s": rng_init_s,
+        "device": {"sm_count": info["sm_count"], "cc": list(info["cc"])},
+        "checksum": checksum,
+    }
+    if base is not None:
+        line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    numba_path = os.path.join(REPO, "profiles", "numba_cuda_baseline.json")
+    if os.path.exists(numba_path):
+        with open(numba_path) as f:
+            line["numba_cuda_baseline"] = json.load(f)
+    print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=5)
+    parser.add_argument("--warmup", type=int, default=3)
+    parser.add_argument("--envs", type=int, default=4096)
+    parser.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    parser.add_argument("--no-cpu-baseline", action="store_true")
+    args = parser.parse_args()
+    assert args.warmup >= 1
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,270 @@
+"""ctypes binding of libreinfocus_b200.so (include/reinfocus_b200.h).
+
+This is the only place the package touches native code. There is no fallback: if the
+library is missing or cannot be loaded, or no sm_100 GPU is visible, the product path
+raises instead of computing anything on the CPU.
+"""
+
+import ctypes
+import os
+import threading
+
+import numpy
+
+from reinfocus_b200 import build as _build
+
+RF_OK = 0
+RF_ERR_INVALID = -1
+RF_ERR_CUDA = -2
+RF_ERR_NOMEM = -3
+RF_ERR_NO_SCENE = -4
+
+ABI_VERSION = 1
+
+STATE_DTYPE = numpy.dtype([("s0", numpy.uint64), ("s1", numpy.uint64)], align=True)
+
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+_vp = ctypes.c_void_p
+
+_SIGNATURES = {
+    "rf_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int]),
+    "rf_destroy": (ctypes.c_int, [_vp]),
+    "rf_last_error": (ctypes.c_char_p, [_vp]),
+    "rf_last_global_error": (ctypes.c_char_p, []),
+    "rf_abi_version": (ctypes.c_int, []),
+    "rf_device_info": (ctypes.c_int, [_vp] + [ctypes.POINTER(ctypes.c_int)] * 4),
+    "rf_launch_count": (ctypes.c_int64, [_vp]),
+    "rf_rng_ensure": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_uint64, _vp]),
+    "rf_rng_reset": (ctypes.c_int, [_vp]),
+    "rf_rng_count": (ctypes.c_int64, [_vp]),
+    "rf_rng_export": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64]),
+    "rf_rng_import": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64]),
+    "rf_rng_init_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_uint64, _vp]),
+    "rf_rng_uniform_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp]),
+    "rf_set_world": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
+    "rf_set_cameras": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _c_float_p, _c_float_p,
+                                      _c_float_p, ctypes.c_double, _vp]),
+    "rf_scene_envs": (ctypes.c_int, [_vp]),
+    "rf_render": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                 _vp, _vp, _vp]),
+    "rf_focus": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
+                                ctypes.c_int, _vp, _vp]),
+    "rf_focus_planes": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
+                                       ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "rf_step_host": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp,
+                                    _vp, _vp]),
+    "rf_step_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    "rf_selftest_checker": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64), _vp]),
+    "rf_measure_fp32_peak": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double),
+                                            ctypes.POINTER(ctypes.c_double)]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class NativeLibraryError(RuntimeError):
+    """libreinfocus_b200.so is missing, stale or unusable. There is no CPU fallback."""
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Loads the native library (no GPU needed for loading and symbol lookup)."""
+
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if not os.path.exists(path):
+            raise NativeLibraryError(
+                f"{path} not found: build it with `python -m reinfocus_b200.build` "
+                "(needs nvcc). reinfocus_b200 has no CPU fallback.")
+        try:
+            lib = ctypes.CDLL(path)
+        except OSError as error:
+            raise NativeLibraryError(f"cannot load {path}: {error}") from error
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as error:
+                raise NativeLibraryError(f"{path} does not export {name}; rebuild it") from error
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.rf_abi_version() != ABI_VERSION:
+            raise NativeLibraryError(
+                f"{path} has ABI {lib.rf_abi_version()}, expected {ABI_VERSION}; rebuild it")
+        _lib = lib
+        return lib
+
+
+def _f3(values):
+    return (ctypes.c_float * 3)(*[float(v) for v in values])
+
+
+def _stream_ptr(stream=None):
+    """The cudaStream_t to launch on: torch's current stream unless one is given."""
+
+    if stream is None:
+        import torch
+
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if hasattr(stream, "cuda_stream"):
+        return ctypes.c_void_p(stream.cuda_stream)
+    return ctypes.c_void_p(int(stream))
+
+
+class Context:
+    """One rf_ctx: a GPU, one cache of RNG states and one scene (= one FastRenderer)."""
+
+    def __init__(self, device: int | None = None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise NativeLibraryError(
+                "no CUDA device visible: reinfocus_b200 runs on B200 (sm_100a) only and has "
+                "no CPU fallback")
+        self._lib = load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        handle = _vp()
+        rc = self._lib.rf_create(ctypes.byref(handle), self.device)
+        if rc != RF_OK:
+            raise NativeLibraryError(self._lib.rf_last_global_error().decode())
+        self._handle = handle
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.rf_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+    # ------------------------------------------------------------------ error mapping
+    def _check(self, rc: int):
+        if rc == RF_OK:
+            return
+        message = self._lib.rf_last_error(self._handle).decode()
+        if rc in (RF_ERR_INVALID, RF_ERR_NO_SCENE):
+            # the reference raises AssertionError when rendering before an update
+            # (graphics/device_data.py:43)
+            raise AssertionError(message)
+        if rc == RF_ERR_NOMEM:
+            raise MemoryError(message)
+        raise RuntimeError(message)
+
+    # ----------------------------------------------------------------------- queries
+    def device_info(self) -> dict:
+        vals = [ctypes.c_int() for _ in range(4)]
+        self._check(self._lib.rf_device_info(self._handle, *[ctypes.byref(v) for v in vals]))
+        return {"sm_count": vals[0].value, "cc": (vals[1].value, vals[2].value),
+                "clock_khz": vals[3].value}
+
+    def launch_count(self) -> int:
+        return int(self._lib.rf_launch_count(self._handle))
+
+    # --------------------------------------------------------------------------- RNG
+    def rng_ensure(self, n_states: int, seed: int = 0, stream=None):
+        self._check(self._lib.rf_rng_ensure(self._handle, int(n_states),
+                                            ctypes.c_uint64(seed & (2**64 - 1)),
+                                            _stream_ptr(stream)))
+
+    def rng_reset(self):
+        self._check(self._lib.rf_rng_reset(self._handle))
+
+    def rng_count(self) -> int:
+        return int(self._lib.rf_rng_count(self._handle))
+
+    def rng_export(self, first: int = 0, n: int | None = None) -> numpy.ndarray:
+        n = self.rng_count() - first if n is None else n
+        out = numpy.empty(n, dtype=STATE_DTYPE)
+        self._check(self._lib.rf_rng_export(self._handle, out.ctypes.data, first, n))
+        return out
+
+    def rng_import(self, states: numpy.ndarray, first: int = 0):
+        states = numpy.ascontiguousarray(states, dtype=STATE_DTYPE)
+        self._check(self._lib.rf_rng_import(self._handle, states.ctypes.data, first, len(states)))
+
+    def rng_init_device(self, d_states_ptr: int, n: int, seed: int, stream=None):
+        self._check(self._lib.rf_rng_init_device(self._handle, _vp(d_states_ptr), int(n),
+                                                 ctypes.c_uint64(seed & (2**64 - 1)),
+                                                 _stream_ptr(stream)))
+
+    def rng_uniform_device(self, d_states_ptr: int, n: int, draws: int, d_out_ptr: int,
+                           stream=None):
+        self._check(self._lib.rf_rng_uniform_device(self._handle, _vp(d_states_ptr), int(n),
+                                                    int(draws), _vp(d_out_ptr),
+                                                    _stream_ptr(stream)))
+
+    # ------------------------------------------------------------------------- scene
+    def set_world(self, world: numpy.ndarray, stream=None):
+        world = numpy.ascontiguousarray(world, dtype=numpy.float32).reshape(-1, 2)
+        self._check(self._lib.rf_set_world(self._handle, len(world), world.ctypes.data,
+                                           _stream_ptr(stream)))
+        # the copy is stream-ordered from pageable memory: CUDA stages it before returning
+
+    def set_cameras(self, cam_dyn: numpy.ndarray, origin, u, v, lens_radius: float, stream=None):
+        cam_dyn = numpy.ascontiguousarray(cam_dyn, dtype=numpy.float32).reshape(-1, 9)
+        self._check(self._lib.rf_set_cameras(self._handle, len(cam_dyn), cam_dyn.ctypes.data,
+                                             _f3(origin), _f3(u), _f3(v), float(lens_radius),
+                                             _stream_ptr(stream)))
+
+    def scene_envs(self) -> int:
+        return int(self._lib.rf_scene_envs(self._handle))
+
+    # ----------------------------------------------------------------------- kernels
+    def render(self, n: int, height: int, width: int, spp: int, d_rgb: int | None,
+               d_gray: int | None, stream=None):
+        self._check(self._lib.rf_render(self._handle, n, height, width, spp, _vp(d_rgb),
+                                        _vp(d_gray), _stream_ptr(stream)))
+
+    def focus(self, n: int, height: int, width: int, d_img: int, channels: int, d_out: int,
+              d_median: int | None = None, d_laplacian: int | None = None, stream=None):
+        self._check(self._lib.rf_focus_planes(self._handle, n, height, width, _vp(d_img),
+                                              channels, _vp(d_out), _vp(d_median),
+                                              _vp(d_laplacian), _stream_ptr(stream)))
+
+    def step_host(self, n: int, height: int, spp: int, h_world: int | None,
+                  h_cam_dyn: int | None, h_focus: int, stream=None):
+        self._check(self._lib.rf_step_host(self._handle, n, height, spp, _vp(h_world),
+                                           _vp(h_cam_dyn), _vp(h_focus), _stream_ptr(stream)))
+
+    def step_device(self, n: int, height: int, spp: int, d_focus: int, stream=None):
+        self._check(self._lib.rf_step_device(self._handle, n, height, spp, _vp(d_focus),
+                                             _stream_ptr(stream)))
+
+    # ------------------------------------------------------------------- self-checks
+    def selftest_checker(self, stream=None) -> int:
+        bad = ctypes.c_int64(-1)
+        self._check(self._lib.rf_selftest_checker(self._handle, ctypes.byref(bad),
+                                                  _stream_ptr(stream)))
+        return bad.value
+
+    def measure_fp32_peak(self) -> tuple[float, float]:
+        tflops, mhz = ctypes.c_double(), ctypes.c_double()
+        self._check(self._lib.rf_measure_fp32_peak(self._handle, ctypes.byref(tflops),
+                                                   ctypes.byref(mhz)))
+        return tflops.value, mhz.value
+
+
+_shared_contexts: dict[int, Context] = {}
+
+
+def shared_context(device: int | None = None) -> Context:
+    """A per-device context for stateless calls (vision.focus_values, make_random_states)."""
+
+    import torch
+
+    device = torch.cuda.current_device() if device is None else int(device)
+    ctx = _shared_contexts.get(device)
+    if ctx is None:
+        ctx = _shared_contexts[device] = Context(device)
+    return ctx

@@ -96,23 +96,14 @@ struct DeviceGuard {
     }
 };
 
-// bit k set: u = k/32 maps to x = fl64(fl64(32 pi) * k/32) < k*pi (see rf_tracer.cuh).
-// long double (x87, 64-bit mantissa) separates x from k*pi unless they are closer than
-// ~1e-17 relative, which is asserted not to happen.
-int checker_below_mask(uint64_t *mask_out) {
-    const double c = 32.0 * 3.14159265358979323846;
-    const long double pi = 3.14159265358979323846264338327950288L;
-    uint64_t mask = 0;
-    for (int k = 1; k <= 32; ++k) {
-        const float u = (float)k / 32.0f;
-        const double x = c * (double)u;
-        const long double d = (long double)x - (long double)k * pi;
-        if (fabsl(d) < 1e-15L * (long double)k) return -1;  // undecidable: never happens
-        if (d < 0) mask |= (1ull << k);
-    }
-    *mask_out = mask;
-    return 0;
-}
+// bit k set: u = k/32 maps to x = fl64(fl64(32 pi) * k/32) < k*pi, i.e. the boundary value
+// still belongs to checker cell k-1 (see rf_tracer.cuh). The 32 comparisons are between a
+// float64 and an irrational: the distances are ~1e-16 (k = 29: 1.2e-18, closer than a
+// long double can resolve), so the table is computed offline with exact rational
+// arithmetic (tests/test_host_side.py::test_checker_boundary_mask recomputes it) and
+// checked on the device against the float64 sin for every float32 u by
+// rf_selftest_checker. x > k*pi only for k in {13, 17, 21, 25, 26, 29}.
+constexpr uint64_t kCheckerBelowMask = 0x1d9dddffeull;
 
 int grow(rf_ctx *ctx, void **ptr, size_t bytes) {
     if (*ptr) {
@@ -282,11 +273,7 @@ int rf_create(rf_ctx **out, int device) {
     }
     std::vector<rf::JumpMatrix> levels(rf::kJumpLevels);
     rf::build_jump_levels(levels.data());
-    uint64_t mask = 0;
-    if (checker_below_mask(&mask) != 0) {
-        delete ctx;
-        return fail(nullptr, RF_ERR_INVALID, "checker boundary table is undecidable");
-    }
+    const uint64_t mask = kCheckerBelowMask;
     auto cleanup = [&](int code) {
         rf_destroy(ctx);
         return code;

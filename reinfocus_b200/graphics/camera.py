@@ -1,0 +1,57 @@
+"""Thin-lens camera parameters (reference graphics/camera.py:94-179 FastCameras).
+
+All cameras share position, orientation, aperture and field of view; only the focus
+distance differs per env. The per-env part is float32 [n, 3, 3] = (lower left corner,
+horizontal, vertical); origin, u, v and the float64 lens radius are passed by value."""
+
+import math
+
+import numpy
+from numpy.typing import NDArray
+
+from reinfocus_b200.graphics import device_data
+from reinfocus_b200.graphics import vector
+
+
+class FastCameras(device_data.DeviceData):
+    def __init__(self, aspect_ratio: float = 1, look_from: vector.V3F = vector.v3f(0, 0, 0),
+                 look_at: vector.V3F = vector.v3f(0, 0, -10),
+                 up: vector.V3F = vector.v3f(0, 1, 0), aperture: float = 0.1,
+                 vfov: float = 30):
+        # pylint: disable=too-many-arguments
+        super().__init__()
+        self._look_from = look_from
+        # reference camera.py:124: a numpy.float64, which is why the kernel's aperture
+        # arithmetic is float64
+        self._half_aperture = numpy.divide(aperture, 2.0)
+        self._half_height = math.tan((vfov * math.pi / 180.0) / 2.0)
+        self._half_width = aspect_ratio * self._half_height
+        self._w = vector.norm_v3f(vector.sub_v3f(look_from, look_at))
+        self._u = vector.norm_v3f(vector.cross_v3f(up, self._w))
+        self._v = vector.cross_v3f(self._w, self._u)
+
+    @property
+    def statics(self):
+        """(origin, u, v, lens radius) passed to the kernel by value."""
+
+        return self._look_from, self._u, self._v, float(self._half_aperture)
+
+    def _make_device_data(self, data: NDArray[numpy.float32]) -> NDArray[numpy.float32]:
+        # reference camera.py:132-179, one env at a time; vectorised here with the same
+        # float32 operations in the same order:
+        #   lower_left = look_from - ((u*(hw*f) + v*(hh*f)) + w*f)
+        #   horizontal = u * (2*hw*f),  vertical = v * (2*hh*f)
+        # Python floats are weak under NumPy 2, so hw, hh, 2*hw, 2*hh enter as float32.
+        f32 = numpy.float32
+        u = numpy.asarray(self._u, dtype=f32)
+        v = numpy.asarray(self._v, dtype=f32)
+        w = numpy.asarray(self._w, dtype=f32)
+        origin = numpy.asarray(self._look_from, dtype=f32)
+        f = data[:, None]
+        total = (u[None, :] * (f32(self._half_width) * f)
+                 + v[None, :] * (f32(self._half_height) * f)) + w[None, :] * f
+        packed = numpy.empty((len(data), 3, 3), dtype=f32)
+        packed[:, 0, :] = origin[None, :] - total
+        packed[:, 1, :] = u[None, :] * (f32(2.0 * self._half_width) * f)
+        packed[:, 2, :] = v[None, :] * (f32(2.0 * self._half_height) * f)
+        return packed

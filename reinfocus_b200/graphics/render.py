@@ -1,0 +1,170 @@
+"""Ray tracing front end (reference graphics/render.py).
+
+``FastRenderer`` keeps the reference's three methods - ``update_targets``,
+``update_focus_planes``, ``render(frame_height) -> uint8 (n, H, H, 3)`` on the host - and
+adds device-resident fast paths so that the per-step caller (FocusObserver) never moves
+images: ``render_device``, ``render_gray_device``, ``focus_values_device`` and
+``step_focus``. All of them launch the same hand-written sm_100a tracer
+(csrc/rf_tracer.cuh) through the C-ABI; there is no CPU path."""
+
+from collections.abc import Collection
+
+import numpy
+from numpy.typing import NDArray
+
+from reinfocus_b200 import _lib
+from reinfocus_b200.graphics import camera
+from reinfocus_b200.graphics import world
+
+
+def make_render_target(frame_shape: tuple[int, ...] = (300, 600)):
+    """A uint8 render target on the GPU (reference render.py:19-28), as a torch tensor."""
+
+    import torch
+
+    return torch.empty(tuple(frame_shape) + (3,), dtype=torch.uint8, device="cuda")
+
+
+class FastRenderer:
+    """Produces images of focus scenes (reference render.py:122-257).
+
+    One instance owns one C-ABI context, i.e. its own cache of per-pixel RNG states: they
+    persist from call to call and are re-created from seed 0 only when a call needs more
+    states than exist (reference render.py:248-257)."""
+
+    def __init__(
+        self,
+        block_shape: tuple[int, int, int] = (1, 16, 16),
+        samples_per_pixel: int = 100,
+        r_size: float = 20,
+        device: int | None = None,
+    ):
+        # block_shape is accepted for signature compatibility; the CUDA kernel picks its
+        # own launch shape (256-thread blocks, consecutive threads along x).
+        self._block_shape = block_shape
+        self._samples_per_pixel = samples_per_pixel
+
+        self._cameras = camera.FastCameras()
+        self._worlds = world.FastWorlds(r_size=r_size)
+
+        self._ctx = _lib.Context(device)
+        self._uploaded_world = -1
+        self._uploaded_cameras = -1
+        self._pinned = {}
+
+    # ------------------------------------------------------------ reference methods
+    def update_targets(self, targets: Collection[float]):
+        """reference render.py:147-154"""
+
+        self._worlds.update(targets)
+
+    def update_focus_planes(self, focus_planes: Collection[float]):
+        """reference render.py:156-163"""
+
+        self._cameras.update(focus_planes)
+
+    def render(self, frame_height: int) -> NDArray[numpy.uint8]:
+        """reference render.py:165-188: uint8 RGB frames (n, H, H, 3) on the host."""
+
+        return self.render_device(frame_height).cpu().numpy()
+
+    # ------------------------------------------------------------------- fast paths
+    @property
+    def context(self) -> _lib.Context:
+        return self._ctx
+
+    @property
+    def samples_per_pixel(self) -> int:
+        return self._samples_per_pixel
+
+    def __len__(self) -> int:
+        return len(self._worlds)
+
+    def _sync_scene(self) -> int:
+        world_data = self._worlds.device_data()  # AssertionError before the first update
+        cam_data = self._cameras.device_data()
+        n = len(self._worlds)
+        assert len(self._cameras) >= n, (
+            f"{n} targets but only {len(self._cameras)} focus planes were set")
+        if self._uploaded_world != self._worlds.version:
+            self._ctx.set_world(world_data)
+            self._uploaded_world = self._worlds.version
+        if self._uploaded_cameras != self._cameras.version:
+            self._ctx.set_cameras(cam_data, *self._cameras.statics)
+            self._uploaded_cameras = self._cameras.version
+        return n
+
+    def render_device(self, frame_height: int):
+        """The frames of ``render`` as a torch uint8 CUDA tensor (n, H, H, 3)."""
+
+        import torch
+
+        n = self._sync_scene()
+        frames = torch.empty((n, frame_height, frame_height, 3), dtype=torch.uint8,
+                             device=f"cuda:{self._ctx.device}")
+        self._ctx.render(n, frame_height, frame_height, self._samples_per_pixel,
+                         frames.data_ptr(), None)
+        return frames
+
+    def render_gray_device(self, frame_height: int):
+        """cv2.cvtColor(frame, RGB2GRAY) of each frame, accumulated in registers: torch
+        uint8 CUDA tensor (n, H, H). Consumes the RNG exactly like ``render``."""
+
+        import torch
+
+        n = self._sync_scene()
+        gray = torch.empty((n, frame_height, frame_height), dtype=torch.uint8,
+                           device=f"cuda:{self._ctx.device}")
+        self._ctx.render(n, frame_height, frame_height, self._samples_per_pixel, None,
+                         gray.data_ptr())
+        return gray
+
+    def focus_values_device(self, frame_height: int):
+        """vision.focus_values(self.render(frame_height)) without leaving the GPU: torch
+        float64 CUDA tensor (n,)."""
+
+        import torch
+
+        n = self._sync_scene()
+        out = torch.empty((n,), dtype=torch.float64, device=f"cuda:{self._ctx.device}")
+        self._ctx.step_device(n, frame_height, self._samples_per_pixel, out.data_ptr())
+        return out
+
+    def step_focus(self, targets: Collection[float], focus_planes: Collection[float],
+                   frame_height: int = 300) -> NDArray[numpy.float64]:
+        """One FocusObserver.observe (reference state_observer.py:377-383) in a single
+        C-ABI call: host targets / focus planes in, host float64 focus values out."""
+
+        import torch
+
+        self.update_targets(targets)
+        self.update_focus_planes(focus_planes)
+        world_data = self._worlds.device_data()
+        cam_data = self._cameras.device_data()
+        n = len(self._worlds)
+        assert len(self._cameras) >= n
+        upload_world = self._uploaded_world != self._worlds.version
+        upload_cameras = self._uploaded_cameras != self._cameras.version
+        if self._uploaded_cameras < 0:
+            # first use: the statics (origin, u, v, lens) travel by value with
+            # rf_set_cameras; afterwards only the dynamic part is copied, inside rf_step_host
+            self._ctx.set_cameras(cam_data, *self._cameras.statics)
+        key = n
+        bufs = self._pinned.get(key)
+        if bufs is None:
+            bufs = (torch.empty((n, 2), dtype=torch.float32).pin_memory(),
+                    torch.empty((n, 9), dtype=torch.float32).pin_memory(),
+                    torch.empty((n,), dtype=torch.float64).pin_memory())
+            self._pinned = {key: bufs}
+        h_world, h_cam, h_focus = bufs
+        if upload_world:
+            h_world.numpy()[...] = world_data
+        if upload_cameras:
+            h_cam.numpy()[...] = cam_data.reshape(n, 9)
+        self._ctx.step_host(n, frame_height, self._samples_per_pixel,
+                            h_world.data_ptr() if upload_world else None,
+                            h_cam.data_ptr() if upload_cameras else None,
+                            h_focus.data_ptr())
+        self._uploaded_world = self._worlds.version
+        self._uploaded_cameras = self._cameras.version
+        return h_focus.numpy().copy()

@@ -1,0 +1,326 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI
+exactly as a user of the reference-shaped Python API would, against the CPU oracle on the
+same seeded inputs, against the committed golden fixtures, and - at full size - through
+size-independent properties. Integer/byte work is compared bit-exactly."""
+
+import glob
+import hashlib
+import os
+
+import numpy
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ctx(torch):
+    from reinfocus_b200 import _lib
+
+    return _lib.shared_context()
+
+
+def _renderer(**kwargs):
+    from reinfocus_b200.graphics import render
+
+    return render.FastRenderer(**kwargs)
+
+
+# --------------------------------------------------------------------------- RNG (a3, a6)
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 0), (3, 5), (255, 0), (256, 1), (257, 2),
+                                    (1000, 12345), (90000, 0), (300007, 2**63 + 5)])
+def test_rng_init_matches_oracle(torch, n, seed):
+    from reinfocus_b200.graphics import random
+
+    states = random.make_random_states(n, seed)
+    assert len(states) == n
+    numpy.testing.assert_array_equal(states.copy_to_host(), oracle.rng_states(n, seed, doubling=True))
+
+
+def test_rng_init_and_draws_match_numba_golden(torch):
+    from reinfocus_b200.graphics import random
+
+    gold = numpy.load(os.path.join(GOLDEN, "rng_numba.npz"))
+    for seed in (0, 1, 12345, 2**63 + 5):
+        states = random.make_random_states(3000, seed)
+        host = states.copy_to_host()
+        got = numpy.stack([host["s0"], host["s1"]], axis=1)
+        numpy.testing.assert_array_equal(got[8:], gold[f"states_seed{seed}"][8:])
+        draws = random.uniform_floats(states, 16).cpu().numpy()
+        numpy.testing.assert_array_equal(draws[:8], gold[f"uniform_seed{seed}"])
+        after = states.copy_to_host()
+        numpy.testing.assert_array_equal(
+            numpy.stack([after["s0"][:8], after["s1"][:8]], axis=1), gold[f"after_seed{seed}"])
+
+
+def test_uniform_draws_match_oracle_including_small_values(torch):
+    """The integer->float32 conversion must round exactly like float32(float64(k) * 2**-53),
+    including results that need the low bits (tiny k) and the rounding-up to 1.0."""
+
+    from reinfocus_b200 import _lib
+    from reinfocus_b200.graphics import random
+
+    # craft states whose next output r = s0 + s1 covers edge patterns
+    outputs = [0, 1 << 11, (1 << 11) - 1, (1 << 64) - 1, (1 << 64) - (1 << 11), 0xFFFFFFFFFFFFF800,
+               0x0000000000FFF800, 0x00000100000007FF, 0x8000008000000000, 0x8000007FFFFFFFFF,
+               0x0000000080000000, 0x00000000FFFFFFFF]
+    host = numpy.zeros(len(outputs), dtype=_lib.STATE_DTYPE)
+    host["s0"] = numpy.array(outputs, dtype=numpy.uint64)
+    states = random.RandomStates(
+        torch.from_numpy(host.view(numpy.uint64).reshape(-1, 2).view(numpy.int64).copy()).cuda())
+    got = random.uniform_floats(states, 3).cpu().numpy()
+    want_states = host.copy()
+    want = numpy.array([[oracle.uniform_float32(want_states, i) for _ in range(3)]
+                        for i in range(len(outputs))], dtype=numpy.float32)
+    numpy.testing.assert_array_equal(got, want)
+    numpy.testing.assert_array_equal(states.copy_to_host(), want_states)
+
+
+# ----------------------------------------------------------------- checker table (a10)
+
+
+def test_checker_table_matches_float64_sin_for_every_float32(ctx):
+    assert ctx.selftest_checker() == 0
+
+
+# ------------------------------------------------------------------------ tracer (a4-a11)
+
+
+CASES = [
+    # targets, focus planes, height, spp
+    ([7.5], [7.5], 16, 2),
+    ([7.5, 7.5], [7.5, 5.0], 32, 8),
+    ([5.0, 10.0, 6.3], [10.0, 5.0, 6.3], 25, 4),  # 1875 pixels: exercises ragged tails
+    ([8.125], [7.9], 8, 100),
+    ([6.0, 9.5, 5.25, 7.0, 8.0], [9.0, 9.5, 5.0, 7.25, 5.5], 75, 7),
+]
+
+
+@pytest.mark.parametrize("targets,planes,height,spp", CASES)
+def test_frames_match_oracle_bit_exactly(torch, targets, planes, height, spp):
+    gpu = _renderer(samples_per_pixel=spp)
+    cpu = oracle.OracleFastRenderer(samples_per_pixel=spp, profile=oracle.PROFILE_GPU)
+    for renderer in (gpu, cpu):
+        renderer.update_targets(targets)
+        renderer.update_focus_planes(planes)
+    for _ in range(2):  # second call: persisted, advanced RNG states
+        got = gpu.render(height)
+        want = cpu.render(height)
+        assert got.dtype == numpy.uint8 and got.shape == (len(targets), height, height, 3)
+        numpy.testing.assert_array_equal(got, want)
+    numpy.testing.assert_array_equal(gpu.context.rng_export(), cpu.states)
+
+
+def test_full_size_frame_matches_oracle(torch):
+    """BASELINE config 1: one env, 300 x 300, 100 samples per pixel."""
+
+    gpu = _renderer()
+    cpu = oracle.OracleFastRenderer(profile=oracle.PROFILE_GPU)
+    for renderer in (gpu, cpu):
+        renderer.update_targets([7.5])
+        renderer.update_focus_planes([7.0])
+    got, want = gpu.render(300), cpu.render(300)
+    mismatch = int((got != want).sum())
+    assert mismatch == 0, f"{mismatch} of {got.size} bytes differ"
+    numpy.testing.assert_array_equal(gpu.context.rng_export(), cpu.states)
+
+
+def test_rng_state_cache_semantics(torch):
+    """reference render.py:248-257: states persist, and are re-created from seed 0 only when
+    a call needs more than exist; a smaller later call reuses the larger cache."""
+
+    gpu = _renderer(samples_per_pixel=3)
+    cpu = oracle.OracleFastRenderer(samples_per_pixel=3, profile=oracle.PROFILE_GPU)
+    for renderer in (gpu, cpu):
+        renderer.update_targets([5.5, 9.0])
+        renderer.update_focus_planes([9.5, 6.0])
+    for height in (8, 12, 8):
+        numpy.testing.assert_array_equal(gpu.render(height), cpu.render(height))
+        assert gpu.context.rng_count() == len(cpu.states)
+    # partial-reset style sub-batch: fewer envs use the states of batch positions 0..k-1
+    for renderer in (gpu, cpu):
+        renderer.update_targets([9.25])
+        renderer.update_focus_planes([5.75])
+    numpy.testing.assert_array_equal(gpu.render(12), cpu.render(12))
+
+
+def test_render_before_update_raises_assertion(torch):
+    renderer = _renderer()
+    with pytest.raises(AssertionError):  # reference device_data.py:43
+        renderer.render(8)
+    renderer.update_targets([7.0])
+    with pytest.raises(AssertionError):
+        renderer.render(8)
+
+
+def test_gray_output_is_cv2_gray_of_rgb(torch):
+    a = _renderer(samples_per_pixel=6)
+    b = _renderer(samples_per_pixel=6)
+    for renderer in (a, b):
+        renderer.update_targets([6.0, 8.5, 9.9])
+        renderer.update_focus_planes([6.5, 5.0, 9.9])
+    rgb = a.render(41)  # 3 * 41 * 41 = 5043 pixels: not a multiple of 4
+    gray = b.render_gray_device(41).cpu().numpy()
+    numpy.testing.assert_array_equal(gray, oracle.gray(rgb))
+
+
+def test_batch_split_property_at_64_envs(torch):
+    """Size-independent property: rendering a batch equals rendering each env alone with
+    that env's slice of the RNG states (env e owns states [e*H*W, (e+1)*H*W))."""
+
+    height, spp, n = 48, 5, 64
+    rng = numpy.random.Generator(numpy.random.PCG64DXSM(1234))
+    targets = rng.uniform(5, 10, n).astype(numpy.float32)
+    planes = rng.uniform(5, 10, n).astype(numpy.float32)
+    whole = _renderer(samples_per_pixel=spp)
+    whole.update_targets(targets)
+    whole.update_focus_planes(planes)
+    frames = whole.render(height)
+    all_states = oracle.rng_states(n * height * height, 0, doubling=True)
+    single = _renderer(samples_per_pixel=spp)
+    for e in (0, 1, 17, 63):
+        single.update_targets(targets[e:e + 1])
+        single.update_focus_planes(planes[e:e + 1])
+        single.context.rng_ensure(height * height)
+        single.context.rng_import(all_states[e * height * height:(e + 1) * height * height])
+        numpy.testing.assert_array_equal(single.render(height)[0], frames[e])
+
+
+# ------------------------------------------------------------------- focus measure (a12)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 7), (7, 1), (2, 2), (3, 3), (4, 9), (5, 5), (16, 16),
+                                   (31, 17), (64, 48), (75, 75), (300, 300), (257, 301), (600, 600)])
+def test_focus_matches_oracle_and_cv2(torch, shape):
+    from reinfocus_b200 import vision
+
+    rng = numpy.random.default_rng(shape[0] * 1000 + shape[1])
+    n = 3
+    base = numpy.linspace(0, 200, shape[1])[None, None, :, None]
+    imgs = (base + rng.integers(0, 56, size=(n,) + shape + (3,))).astype(numpy.uint8)
+    got = numpy.array(vision.focus_values(imgs))
+    want = oracle.focus_values(imgs)
+    numpy.testing.assert_array_equal(got, want)  # same exact integer sums, same division
+    gray = oracle.gray(imgs)
+    got_gray = vision.focus_values_device(torch.from_numpy(gray).cuda()).cpu().numpy()
+    numpy.testing.assert_array_equal(got_gray, want)
+    try:
+        import cv2
+    except ImportError:
+        return
+    ref = [cv2.Laplacian(cv2.medianBlur(cv2.cvtColor(i, cv2.COLOR_RGB2GRAY), 3), cv2.CV_8U).var()
+           for i in imgs]
+    numpy.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13)
+
+
+def test_focus_planes_match_oracle(ctx, torch):
+    rng = numpy.random.default_rng(3)
+    gray = rng.integers(0, 256, size=(4, 37, 53), dtype=numpy.uint8)
+    d_gray = torch.from_numpy(gray).cuda()
+    out = torch.empty(4, dtype=torch.float64, device="cuda")
+    med = torch.empty_like(d_gray)
+    lap = torch.empty_like(d_gray)
+    ctx.focus(4, 37, 53, d_gray.data_ptr(), 1, out.data_ptr(), med.data_ptr(), lap.data_ptr())
+    want, wmed, wlap = oracle.focus_values_gray(gray, planes=True)
+    numpy.testing.assert_array_equal(med.cpu().numpy(), wmed)
+    numpy.testing.assert_array_equal(lap.cpu().numpy(), wlap)
+    numpy.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
+def test_focus_reference_vision_tests(torch):
+    """reference tests/vision_test.py:14-34."""
+
+    from reinfocus_b200 import vision
+
+    assert vision.focus_value(numpy.zeros((5, 5, 3), dtype=numpy.uint8)) == 0.0
+    assert vision.focus_value(numpy.ones((5, 5, 3), dtype=numpy.uint8)) == 0.0
+    checker = numpy.zeros((10, 10, 3), dtype=numpy.uint8)
+    checker[::2, ::2] = 255
+    checker[1::2, 1::2] = 255
+    assert vision.focus_value(checker) == pytest.approx(16230.240000000005, rel=1e-14)
+
+
+def test_focus_golden_cv2(torch):
+    from reinfocus_b200 import vision
+
+    gold = numpy.load(os.path.join(GOLDEN, "focus_cv2.npz"))
+    for name in gold["small_names"]:
+        got = vision.focus_value(gold[f"img_{name}"])
+        assert got == pytest.approx(float(gold[f"fv_{name}"]), rel=1e-13, abs=1e-13), name
+    numpy.testing.assert_allclose(vision.focus_values(gold["batch_imgs"]), gold["batch_fv"], rtol=1e-13)
+
+
+# ----------------------------------------------------------------------- fused step (a13)
+
+
+def test_step_focus_equals_render_then_focus(torch):
+    targets = [5.5, 7.5, 9.0, 6.25]
+    planes = [5.75, 7.5, 6.0, 9.5]
+    fused = _renderer(samples_per_pixel=9)
+    cpu = oracle.OracleFastRenderer(samples_per_pixel=9, profile=oracle.PROFILE_GPU)
+    cpu.update_targets(targets)
+    cpu.update_focus_planes(planes)
+    for _ in range(2):
+        got = fused.step_focus(targets, planes, 60)
+        want = oracle.focus_values(cpu.render(60))
+        numpy.testing.assert_array_equal(got, want)
+    # device-resident variant, same numbers for the next call
+    got = fused.focus_values_device(60).cpu().numpy()
+    numpy.testing.assert_array_equal(got, oracle.focus_values(cpu.render(60)))
+
+
+def test_focus_is_monotonic_towards_the_target(torch):
+    """reference tests/vision_test.py:40-56."""
+
+    from reinfocus_b200 import vision
+
+    renderer = _renderer()
+    renderer.update_targets([10] * 5)
+    renderer.update_focus_planes([40, 20, 10, 5, 1])
+    fv = vision.focus_values(renderer.render(100))
+    assert fv[0] < fv[1] < fv[2] > fv[3] > fv[4]
+
+
+# --------------------------------------------- golden vectors from the reference on a B200
+
+
+def _gpu_golden():
+    return sorted(glob.glob(os.path.join(GOLDEN, "gpu_render_*.npz")))
+
+
+@pytest.mark.parametrize("path", _gpu_golden(), ids=lambda p: os.path.basename(p)[11:-4])
+def test_frames_match_reference_numba_cuda_golden(torch, path):
+    from reinfocus_b200 import vision
+
+    gold = numpy.load(path)
+    renderer = _renderer(samples_per_pixel=int(gold["spp"]), r_size=float(gold["r_size"]))
+    for i in range(int(gold["n_calls"])):
+        renderer.update_targets(gold[f"targets_{i}"])
+        renderer.update_focus_planes(gold[f"planes_{i}"])
+        frames = renderer.render(int(gold[f"height_{i}"]))
+        assert renderer.context.rng_count() == int(gold[f"n_states_{i}"])
+        if f"frames_{i}" in gold:
+            want = gold[f"frames_{i}"]
+            mismatch = int((frames != want).sum())
+            assert mismatch == 0, f"call {i}: {mismatch} of {want.size} bytes differ"
+        else:
+            assert hashlib.sha256(frames.tobytes()).hexdigest() == str(gold[f"sha256_{i}"])
+        numpy.testing.assert_allclose(vision.focus_values(frames), gold[f"focus_{i}"], rtol=1e-13)
+        head = renderer.context.rng_export(0, 64)
+        numpy.testing.assert_array_equal(
+            numpy.stack([head["s0"], head["s1"]], axis=1), gold[f"states_head_{i}"])

@@ -83,6 +83,37 @@ def test_sim_profile_reproduces_reference_under_cudasim(path):
         numpy.testing.assert_allclose(oracle.focus_values(frames), gold[f"focus_{i}"], rtol=1e-14)
 
 
+def _gpu_cases():
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "gpu_render_*.npz")))
+
+
+@pytest.mark.parametrize("path", _gpu_cases(), ids=lambda p: os.path.basename(p)[11:-4])
+def test_gpu_profile_reproduces_reference_numba_cuda_on_b200(path):
+    """Golden vectors recorded by oracle/gen_golden_gpu.py from the unmodified reference's
+    compiled numba-CUDA kernel on a B200: frames bit-exact (or sha256-equal for the large
+    ones), focus values as cv2 + numpy.var computed them, RNG states after each call."""
+
+    import hashlib
+
+    gold = numpy.load(path)
+    renderer = oracle.OracleFastRenderer(samples_per_pixel=int(gold["spp"]),
+                                         r_size=float(gold["r_size"]),
+                                         profile=oracle.PROFILE_GPU)
+    for i in range(int(gold["n_calls"])):
+        renderer.update_targets(gold[f"targets_{i}"])
+        renderer.update_focus_planes(gold[f"planes_{i}"])
+        frames = renderer.render(int(gold[f"height_{i}"]))
+        assert len(renderer.states) == int(gold[f"n_states_{i}"])
+        if f"frames_{i}" in gold:
+            numpy.testing.assert_array_equal(frames, gold[f"frames_{i}"])
+        else:
+            assert hashlib.sha256(frames.tobytes()).hexdigest() == str(gold[f"sha256_{i}"])
+            numpy.testing.assert_array_equal(frames[:1], gold[f"frames_{i}_first"])
+        numpy.testing.assert_allclose(oracle.focus_values(frames), gold[f"focus_{i}"], rtol=1e-14)
+        head = numpy.stack([renderer.states["s0"][:64], renderer.states["s1"][:64]], axis=1)
+        numpy.testing.assert_array_equal(head, gold[f"states_head_{i}"])
+
+
 def test_gpu_profile_differs_only_slightly_from_sim_profile():
     """The two typings of the same algorithm: same draws, a handful of 1-level flips."""
 
