@@ -147,10 +147,26 @@ int rf_step_device(rf_ctx *ctx, int n, int H, int spp, double *d_focus, void *st
 /* -------------------------------------------------------------------------------------
  * Self-checks and measurement helpers (used by tests/ and bench.py).
  * ----------------------------------------------------------------------------------- */
-/* Exhaustively compares the kernel's table-based checkerboard cell test against
- * sin(32*pi*u) evaluated in float64 on the device for every float32 u in [0, 1];
- * *mismatches receives the count (must be 0). */
-int rf_selftest_checker(rf_ctx *ctx, int64_t *mismatches, void *stream);
+/* Exhaustive device-side checks of the arithmetic shortcuts the tracer takes; *mismatches
+ * receives the number of inputs on which the shortcut differs from the literal reference
+ * expression (must be 0):
+ *   RF_SELFTEST_CHECKER     table-based checkerboard cell vs sin(32*pi*u) in float64, for
+ *                           every float32 u in [0, 1];
+ *   RF_SELFTEST_PIXEL_DIV   hoisted-reciprocal float64 division vs __ddiv_rn for
+ *                           float32((x + U) / arg), every x in [0, arg), every float32 U in
+ *                           [0, 1] (arg = frame width or height);
+ *   RF_SELFTEST_INV_LENGTH  branch-free 1/sqrt-length vs __frcp_rn(__fsqrt_rn()) for every
+ *                           float32 in [2^-60, 2^60]. */
+enum { RF_SELFTEST_CHECKER = 0, RF_SELFTEST_PIXEL_DIV = 1, RF_SELFTEST_INV_LENGTH = 2 };
+int rf_selftest(rf_ctx *ctx, int which, int arg, int64_t *mismatches, void *stream);
+/* Options. RF_OPT_FORCE_GENERIC = 1 makes rf_render use the literal any-camera kernel even
+ * when the specialised default-camera kernel applies (A/B parity tests). */
+enum { RF_OPT_FORCE_GENERIC = 0 };
+int rf_set_option(rf_ctx *ctx, int option, int value);
+/* Introspection. RF_INFO_LAST_TRACE_KERNEL: 1 if the last rf_render used the specialised
+ * kernel, 0 for the generic one, -1 before any render. */
+enum { RF_INFO_LAST_TRACE_KERNEL = 0 };
+int rf_get_info(const rf_ctx *ctx, int what);
 /* Measures the FP32 FFMA peak of this GPU (dependent-chain-free FFMA loop on all SMs);
  * returns TFLOP/s counting 2 flop per FFMA. */
 int rf_measure_fp32_peak(rf_ctx *ctx, double *tflops, double *sm_clock_mhz_seen);

@@ -19,7 +19,11 @@ RF_ERR_CUDA = -2
 RF_ERR_NOMEM = -3
 RF_ERR_NO_SCENE = -4
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+
+SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH = 0, 1, 2
+OPT_FORCE_GENERIC = 0
+INFO_LAST_TRACE_KERNEL = 0
 
 STATE_DTYPE = numpy.dtype([("s0", numpy.uint64), ("s1", numpy.uint64)], align=True)
 
@@ -54,7 +58,10 @@ _SIGNATURES = {
     "rf_step_host": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp,
                                     _vp, _vp]),
     "rf_step_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
-    "rf_selftest_checker": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64), _vp]),
+    "rf_selftest": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int,
+                                   ctypes.POINTER(ctypes.c_int64), _vp]),
+    "rf_set_option": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    "rf_get_info": (ctypes.c_int, [_vp, ctypes.c_int]),
     "rf_measure_fp32_peak": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double),
                                             ctypes.POINTER(ctypes.c_double)]),
 }
@@ -242,11 +249,20 @@ class Context:
                                              _stream_ptr(stream)))
 
     # ------------------------------------------------------------------- self-checks
-    def selftest_checker(self, stream=None) -> int:
+    def selftest(self, which: int, arg: int = 0, stream=None) -> int:
         bad = ctypes.c_int64(-1)
-        self._check(self._lib.rf_selftest_checker(self._handle, ctypes.byref(bad),
-                                                  _stream_ptr(stream)))
+        self._check(self._lib.rf_selftest(self._handle, which, arg, ctypes.byref(bad),
+                                          _stream_ptr(stream)))
         return bad.value
+
+    def selftest_checker(self, stream=None) -> int:
+        return self.selftest(SELFTEST_CHECKER, 0, stream)
+
+    def set_option(self, option: int, value: int):
+        self._check(self._lib.rf_set_option(self._handle, option, value))
+
+    def last_trace_kernel(self) -> int:
+        return int(self._lib.rf_get_info(self._handle, INFO_LAST_TRACE_KERNEL))
 
     def measure_fp32_peak(self) -> tuple[float, float]:
         tflops, mhz = ctypes.c_double(), ctypes.c_double()

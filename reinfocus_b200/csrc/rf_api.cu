@@ -16,7 +16,7 @@
 #include "rf_rng.cuh"
 #include "rf_tracer.cuh"
 
-#define RF_ABI_VERSION 1
+#define RF_ABI_VERSION 2
 
 namespace {
 
@@ -55,6 +55,9 @@ struct rf_ctx {
     double *d_focus = nullptr;
     int cap_focus_out = 0;
     unsigned long long *d_misc = nullptr;  // small scratch (selftests)
+
+    bool force_generic = false;  // RF_OPT_FORCE_GENERIC
+    int last_kernel = -1;        // 0 generic, 1 fast (introspection for tests)
 };
 
 namespace {
@@ -167,7 +170,16 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
     p.total = (int64_t)n * H * W;
     const int64_t blocks = (p.total + rf::kTraceThreads - 1) / rf::kTraceThreads;
     if (blocks > 0x7fffffffLL) return fail(ctx, RF_ERR_INVALID, "render batch too large");
-    rf::trace_kernel<<<(unsigned)blocks, rf::kTraceThreads, 0, stream>>>(p);
+    // the specialised kernel covers the camera every reference env uses (FastCameras
+    // defaults, reference camera.py:99-130); anything else runs the literal statement
+    const bool fast = !ctx->force_generic && ctx->u[0] == 1.0f && ctx->u[1] == 0.0f &&
+                      ctx->u[2] == 0.0f && ctx->v[0] == 0.0f && ctx->v[1] == 1.0f &&
+                      ctx->v[2] == 0.0f && ctx->lens_radius == 0.05;
+    if (fast)
+        rf::trace_kernel<true><<<(unsigned)blocks, rf::kTraceThreads, 0, stream>>>(p);
+    else
+        rf::trace_kernel<false><<<(unsigned)blocks, rf::kTraceThreads, 0, stream>>>(p);
+    ctx->last_kernel = fast ? 1 : 0;
     ctx->launches++;
     RF_CUDA(ctx, cudaGetLastError());
     return RF_OK;
@@ -531,12 +543,47 @@ int rf_step_host(rf_ctx *ctx, int n, int H, int spp, const float *h_world, const
 
 // ---------------------------------------------------------------------------- self-checks
 
-int rf_selftest_checker(rf_ctx *ctx, int64_t *mismatches, void *stream) {
-    RF_REQUIRE(ctx, ctx != nullptr && mismatches, "rf_selftest_checker: NULL argument");
+int rf_set_option(rf_ctx *ctx, int option, int value) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_set_option: ctx is NULL");
+    switch (option) {
+        case RF_OPT_FORCE_GENERIC:
+            ctx->force_generic = value != 0;
+            return RF_OK;
+        default:
+            return fail(ctx, RF_ERR_INVALID, "rf_set_option: unknown option %d", option);
+    }
+}
+
+int rf_get_info(const rf_ctx *ctx, int what) {
+    if (!ctx) return -1;
+    switch (what) {
+        case RF_INFO_LAST_TRACE_KERNEL:
+            return ctx->last_kernel;
+        default:
+            return -1;
+    }
+}
+
+int rf_selftest(rf_ctx *ctx, int which, int arg, int64_t *mismatches, void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr && mismatches, "rf_selftest: NULL argument");
     DeviceGuard guard(ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
     RF_CUDA(ctx, cudaMemsetAsync(ctx->d_misc, 0, sizeof(unsigned long long), s));
-    rf::checker_selftest_kernel<<<ctx->prop.multiProcessorCount * 8, 256, 0, s>>>(ctx->d_misc);
+    const int blocks = ctx->prop.multiProcessorCount * 8;
+    switch (which) {
+        case RF_SELFTEST_CHECKER:
+            rf::checker_selftest_kernel<<<blocks, 256, 0, s>>>(ctx->d_misc);
+            break;
+        case RF_SELFTEST_PIXEL_DIV:
+            RF_REQUIRE(ctx, arg > 0 && arg <= 16384, "rf_selftest: frame size out of range");
+            rf::pixel_div_selftest_kernel<<<blocks, 256, 0, s>>>(arg, ctx->d_misc);
+            break;
+        case RF_SELFTEST_INV_LENGTH:
+            rf::inv_length_selftest_kernel<<<blocks, 256, 0, s>>>(ctx->d_misc);
+            break;
+        default:
+            return fail(ctx, RF_ERR_INVALID, "rf_selftest: unknown test %d", which);
+    }
     ctx->launches++;
     RF_CUDA(ctx, cudaGetLastError());
     unsigned long long bad = 0;

@@ -43,6 +43,54 @@ __device__ __forceinline__ float rng_uniform(RngState &s) {
     return __ull2float_rn(r >> 11) * 0x1p-53f;
 }
 
+// The same generator on explicit 32-bit halves, the form the tracer's hot loops use.
+// On sm_100a the ALU pipe (LOP3 / SHF / IADD3: 64 lanes/clk/SM) is what bounds
+// xoroshiro128+, so the formulation minimises ALU-pipe instructions: rotations are single
+// funnel shifts, the carry-in add and the plain left shift are left to IMAD (FMA pipe),
+// and the ">> 11" of the output is a mask (one LOP3 instead of two shifts) whose 2^11 is
+// folded into the float scale.
+struct Rng32 {
+    uint32_t a, b, c, d;  // s0 = b:a, s1 = d:c
+};
+
+__device__ __forceinline__ Rng32 rng32_load(const RngState *p) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    return Rng32{v.x, v.y, v.z, v.w};
+}
+
+__device__ __forceinline__ void rng32_store(RngState *p, const Rng32 &s) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(s.a, s.b, s.c, s.d);
+}
+
+// Advances the state and returns RN_float32(k) * 2^11 where k = (s0 + s1) >> 11, i.e. the
+// uniform sample scaled by 2^64: uniform = result * 2^-64 (exact scaling).
+__device__ __forceinline__ float rng32_next_scaled(Rng32 &s) {
+    uint32_t rl, rh;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;"
+        : "=r"(rl), "=r"(rh)
+        : "r"(s.a), "r"(s.c), "r"(s.b), "r"(s.d));
+    const uint32_t tl = s.a ^ s.c, th = s.b ^ s.d;
+    // rotl(s0, 55) = rotr(s0, 9)
+    const uint32_t ql = __funnelshift_r(s.a, s.b, 9), qh = __funnelshift_r(s.b, s.a, 9);
+    // t << 14
+    const uint32_t ul = tl << 14, uh = __funnelshift_l(tl, th, 14);
+    s.a = ql ^ tl ^ ul;
+    s.b = qh ^ th ^ uh;
+    // rotl(t, 36) = swap halves, rotl 4
+    s.c = __funnelshift_l(tl, th, 4);
+    s.d = __funnelshift_l(th, tl, 4);
+    const uint64_t k = ((uint64_t)rh << 32) | (rl & 0xfffff800u);
+    return __ull2float_rn(k);
+}
+
+__device__ __forceinline__ float rng32_uniform(Rng32 &s) { return rng32_next_scaled(s) * 0x1p-64f; }
+
+// 2 * uniform - 1 in one fma: RN(RN(k) * 2^-52 - 1) == fma(uniform, 2, -1) because both
+// scalings are exact
+__device__ __forceinline__ float rng32_signed_unit(Rng32 &s) {
+    return __fmaf_rn(rng32_next_scaled(s), 0x1p-63f, -1.0f);
+}
+
 // numba/cuda/random.py init_xoroshiro128p_state (SplitMix64 of the seed in both words)
 inline RngState rng_seed_state(uint64_t seed) {
     uint64_t z = seed + 0x9E3779B97F4A7C15ull;
@@ -132,9 +180,9 @@ rng_double_kernel(RngState *__restrict__ states, const JumpMatrix *__restrict__ 
 __global__ void rng_uniform_kernel(RngState *states, int64_t n, int draws, float *out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    RngState s = states[i];
-    for (int k = 0; k < draws; ++k) out[i * draws + k] = rng_uniform(s);
-    states[i] = s;
+    Rng32 s = rng32_load(states + i);
+    for (int k = 0; k < draws; ++k) out[i * draws + k] = rng32_uniform(s);
+    rng32_store(states + i, s);
 }
 
 }  // namespace rf

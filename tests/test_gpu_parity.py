@@ -98,6 +98,68 @@ def test_checker_table_matches_float64_sin_for_every_float32(ctx):
     assert ctx.selftest_checker() == 0
 
 
+@pytest.mark.parametrize("size", [300, 7, 75, 600])
+def test_hoisted_reciprocal_division_equals_ddiv_for_every_input(ctx, size):
+    """float32((x + U) / size) for every pixel coordinate x and every float32 U in [0, 1]."""
+
+    from reinfocus_b200 import _lib
+
+    assert ctx.selftest(_lib.SELFTEST_PIXEL_DIV, size) == 0
+
+
+def test_branch_free_inverse_length_equals_intrinsics_for_every_input(ctx):
+    from reinfocus_b200 import _lib
+
+    assert ctx.selftest(_lib.SELFTEST_INV_LENGTH) == 0
+
+
+@pytest.mark.parametrize("targets,planes,height,spp", [
+    ([7.5, 5.0, 10.0, 6.3], [7.5, 10.0, 5.0, 6.3], 40, 12),
+    ([9.0, 5.5], [5.25, 9.75], 97, 5),
+])
+def test_specialised_kernel_equals_literal_kernel(torch, targets, planes, height, spp):
+    """A/B on the device: the default-camera kernel (float32 shortcuts) against the
+    any-camera kernel (the literal float64-typed statement), same scene, same states."""
+
+    from reinfocus_b200 import _lib
+
+    fast, literal = _renderer(samples_per_pixel=spp), _renderer(samples_per_pixel=spp)
+    literal.context.set_option(_lib.OPT_FORCE_GENERIC, 1)
+    for renderer in (fast, literal):
+        renderer.update_targets(targets)
+        renderer.update_focus_planes(planes)
+    for _ in range(2):
+        a, b = fast.render(height), literal.render(height)
+        numpy.testing.assert_array_equal(a, b)
+    assert fast.context.last_trace_kernel() == 1 and literal.context.last_trace_kernel() == 0
+    numpy.testing.assert_array_equal(fast.context.rng_export(), literal.context.rng_export())
+
+
+def test_literal_kernel_handles_a_non_default_camera(torch):
+    """Any origin / basis / lens radius goes through the literal kernel and still matches
+    the oracle bit for bit."""
+
+    from reinfocus_b200 import _lib
+
+    n, height, spp = 2, 33, 6
+    world = oracle.pack_world([6.0, 8.0])
+    statics = oracle.CameraStatics(look_from=(0.3, -0.2, 0.5), look_at=(0.1, 0.4, -9.0),
+                                   up=(0.1, 1.0, 0.05), aperture=0.23, vfov=28)
+    cam = oracle.pack_cameras([6.5, 7.5], statics)
+    ctx = _lib.Context()
+    ctx.set_world(world)
+    ctx.set_cameras(cam, statics.look_from, statics.u, statics.v, float(statics.half_aperture))
+    frames = torch.empty((n, height, height, 3), dtype=torch.uint8, device="cuda")
+    ctx.render(n, height, height, spp, frames.data_ptr(), None)
+    assert ctx.last_trace_kernel() == 0
+    states = oracle.rng_states(n * height * height, 0)
+    want = oracle.render_fast(world, cam, height, spp, states, oracle.PROFILE_GPU,
+                              statics.look_from, statics.u, statics.v,
+                              float(statics.half_aperture))
+    numpy.testing.assert_array_equal(frames.cpu().numpy(), want)
+    numpy.testing.assert_array_equal(ctx.rng_export(), states)
+
+
 # ------------------------------------------------------------------------ tracer (a4-a11)
 
 

@@ -1,0 +1,113 @@
+// Micro-benchmark: throughput of xoroshiro128+ "next + uniform float32" formulations on
+// sm_100a. All variants must produce bit-identical draws; the benchmark checks that and
+// reports draws/s. Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o rng_microbench
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+struct S { uint64_t s0, s1; };
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+// v1: plain 64-bit C (what the first tracer used)
+__device__ __forceinline__ float draw_v1(uint64_t &s0, uint64_t &s1) {
+    const uint64_t r = s0 + s1;
+    uint64_t t = s1 ^ s0;
+    s0 = rotl64(s0, 55) ^ t ^ (t << 14);
+    s1 = rotl64(t, 36);
+    return __ull2float_rn(r >> 11) * 0x1p-53f;
+}
+
+// v2: explicit 32-bit halves with funnel shifts (all ALU pipe), masked I2F
+struct H { uint32_t a, b, c, d; };  // s0 = b:a, s1 = d:c
+__device__ __forceinline__ float draw_v2(H &s) {
+    uint32_t rl, rh;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=r"(rl), "=r"(rh) : "r"(s.a), "r"(s.c), "r"(s.b), "r"(s.d));
+    const uint32_t tl = s.a ^ s.c, th = s.b ^ s.d;
+    // rotl55 = rotr9
+    const uint32_t ql = __funnelshift_r(s.a, s.b, 9), qh = __funnelshift_r(s.b, s.a, 9);
+    const uint32_t ul = tl << 14, uh = __funnelshift_l(tl, th, 14);
+    s.a = ql ^ tl ^ ul;
+    s.b = qh ^ th ^ uh;
+    // rotl36 = swap + rotl4
+    s.c = __funnelshift_l(tl, th, 4);
+    s.d = __funnelshift_l(th, tl, 4);
+    const uint64_t k = ((uint64_t)rh << 32) | (rl & 0xfffff800u);
+    return __ull2float_rn(k) * 0x1p-64f;
+}
+
+// v3: shifts as 32x32->64 multiplies by run-time powers of two (IMAD.WIDE on the FMA pipe),
+// xors on the ALU pipe
+struct M { uint32_t m23, m14, m4, one; };
+__device__ __forceinline__ float draw_v3(H &s, const M m) {
+    const uint64_t sum = (uint64_t)s.a * m.one + (((uint64_t)s.d << 32) | s.c);  // IMAD.WIDE acc
+    const uint32_t rl = (uint32_t)sum, rh = (uint32_t)(sum >> 32) + s.b;
+    const uint32_t tl = s.a ^ s.c, th = s.b ^ s.d;
+    const uint64_t A = (uint64_t)s.a * m.m23, B = (uint64_t)s.b * m.m23;
+    const uint64_t C = (uint64_t)tl * m.m14;
+    const uint32_t D = th * m.m14;
+    const uint64_t E = (uint64_t)tl * m.m4, F = (uint64_t)th * m.m4;
+    s.a = (uint32_t)(A >> 32) ^ (uint32_t)B ^ tl ^ (uint32_t)C;
+    s.b = (uint32_t)(B >> 32) ^ (uint32_t)A ^ th ^ (uint32_t)(C >> 32) ^ D;
+    s.c = (uint32_t)F | (uint32_t)(E >> 32);
+    s.d = (uint32_t)E | (uint32_t)(F >> 32);
+    const uint64_t k = ((uint64_t)rh << 32) | (rl & 0xfffff800u);
+    return __ull2float_rn(k) * 0x1p-64f;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) bench(const S *in, float *out, int draws, M m) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const S st = in[i];
+    float acc = 0.f;
+    if (V == 1) {
+        uint64_t s0 = st.s0, s1 = st.s1;
+        for (int k = 0; k < draws; ++k) acc += draw_v1(s0, s1);
+    } else {
+        H h{(uint32_t)st.s0, (uint32_t)(st.s0 >> 32), (uint32_t)st.s1, (uint32_t)(st.s1 >> 32)};
+        for (int k = 0; k < draws; ++k) acc += (V == 2) ? draw_v2(h) : draw_v3(h, m);
+    }
+    out[i] = acc;
+}
+
+int main() {
+    const int threads = 148 * 8 * 256, draws = 20000;
+    S *h = new S[threads];
+    uint64_t z = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < threads; ++i) {
+        z = z * 6364136223846793005ull + 1442695040888963407ull;
+        h[i].s0 = z;
+        z = z * 6364136223846793005ull + 1442695040888963407ull;
+        h[i].s1 = z;
+    }
+    S *d_in; float *d_out[3];
+    cudaMalloc(&d_in, sizeof(S) * threads);
+    cudaMemcpy(d_in, h, sizeof(S) * threads, cudaMemcpyHostToDevice);
+    for (int v = 0; v < 3; ++v) cudaMalloc(&d_out[v], sizeof(float) * threads);
+    const M m{1u << 23, 1u << 14, 1u << 4, 1u};
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float *host[3];
+    for (int v = 0; v < 3; ++v) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(e0);
+            if (v == 0) bench<1><<<threads / 256, 256>>>(d_in, d_out[v], draws, m);
+            if (v == 1) bench<2><<<threads / 256, 256>>>(d_in, d_out[v], draws, m);
+            if (v == 2) bench<3><<<threads / 256, 256>>>(d_in, d_out[v], draws, m);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (rep) best = ms < best ? ms : best;
+        }
+        host[v] = new float[threads];
+        cudaMemcpy(host[v], d_out[v], sizeof(float) * threads, cudaMemcpyDeviceToHost);
+        const double dps = (double)threads * draws / (best * 1e-3);
+        printf("v%d: %.3f ms  %.1f Gdraws/s  %.2f cycles/draw/SMSP-warp @1.9GHz (err=%s)\n", v + 1, best,
+               dps / 1e9, 148.0 * 4 * 1.9e9 * 32 / dps, cudaGetErrorString(cudaGetLastError()));
+    }
+    int bad2 = 0, bad3 = 0;
+    for (int i = 0; i < threads; ++i) { bad2 += host[0][i] != host[1][i]; bad3 += host[0][i] != host[2][i]; }
+    printf("mismatch v2=%d v3=%d\n", bad2, bad3);
+    return 0;
+}
