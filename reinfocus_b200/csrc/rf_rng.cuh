@@ -74,8 +74,10 @@ __device__ __forceinline__ float rng32_next_scaled(Rng32 &s) {
     const uint32_t ql = __funnelshift_r(s.a, s.b, 9), qh = __funnelshift_r(s.b, s.a, 9);
     // t << 14
     const uint32_t ul = tl << 14, uh = __funnelshift_l(tl, th, 14);
-    s.a = ql ^ tl ^ ul;
-    s.b = qh ^ th ^ uh;
+    // three-input xors as single LOP3s (left to itself nvcc re-associates them through
+    // s0 ^ s1 to shorten the dependency chain, which costs two more ALU instructions)
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s.a) : "r"(ql), "r"(tl), "r"(ul));
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s.b) : "r"(qh), "r"(th), "r"(uh));
     // rotl(t, 36) = swap halves, rotl 4
     s.c = __funnelshift_l(tl, th, 4);
     s.d = __funnelshift_l(th, tl, 4);

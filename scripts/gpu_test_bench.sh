@@ -1,0 +1,11 @@
+# GPU parity tests + smoke + bench on one B200 (run under gpurun). usage: bash scripts/gpu_test_bench.sh <tag>
+TAG=${1:-run}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/${TAG}_smoke.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?" >> gpurun_out/${TAG}_bench.err
+tail -6 gpurun_out/${TAG}_pytest.log; tail -2 gpurun_out/${TAG}_smoke.log; tail -2 gpurun_out/${TAG}_bench.err; python - <<PY
+import json
+d=json.load(open("gpurun_out/${TAG}_bench.json"))
+print({k:d[k] for k in ("value","ms_per_step","rays_per_s")}, d["e2e"], d["roofline"]["launch_ms"], d["roofline_focus"]["launch_ms"], d["clocks"])
+PY
