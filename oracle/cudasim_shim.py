@@ -61,9 +61,34 @@ def install(reference_root: str = REFERENCE_ROOT, with_gym_stub: bool = True) ->
 
     if with_gym_stub:
         install_gym_stub()
+        install_plot_stub()
 
     if reference_root not in sys.path:
         sys.path.insert(0, reference_root)
+
+
+def install_plot_stub() -> None:
+    """matplotlib is imported at module import time by the reference's
+    environments/episode_visualizer.py:6-10 (and therefore by anything that imports the env
+    classes); it is not installed offline. An empty stand-in is enough to import - nothing
+    in the golden-vector harness plots."""
+
+    try:
+        import matplotlib  # noqa: F401
+
+        return
+    except ImportError:
+        pass
+    import types
+
+    root = types.ModuleType("matplotlib")
+    root.colormaps = {}
+    colors = types.ModuleType("matplotlib.colors")
+    colors.Colormap = object
+    pyplot = types.ModuleType("matplotlib.pyplot")
+    root.colors, root.pyplot = colors, pyplot
+    sys.modules.update({"matplotlib": root, "matplotlib.colors": colors,
+                        "matplotlib.pyplot": pyplot})
 
 
 def install_gym_stub() -> None:

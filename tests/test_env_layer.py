@@ -1,0 +1,79 @@
+"""CPU tests of the env layer (reinfocus_b200.environments) against golden sequences that
+the unmodified reference classes produced (oracle/gen_golden_env.py sim): same compositions
+of strategy objects, same seeded initial states, same scripted actions. The focus value
+comes from an analytic stand-in here (the real FocusObserver needs the GPU; its sequences
+are covered by the -m gpu tests), so this pins everything around the hot path: transformer,
+enders, rewarders, Delta/Normalized observers and the same-step auto-reset. All comparisons
+are exact."""
+
+import os
+
+import numpy
+import pytest
+
+from oracle import gen_golden_env
+from reinfocus_b200 import gym_compat, histories
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def modules():
+    return gen_golden_env._Modules("reinfocus_b200")
+
+
+@pytest.mark.parametrize("name", sorted(gen_golden_env.sim_cases()))
+def test_env_sequences_equal_the_reference(modules, name):
+    gold = numpy.load(os.path.join(GOLDEN, f"env_sim_{name}.npz"))
+    focus_cls = gen_golden_env.make_analytic_observer(modules.state_observer)
+    env, actions, vector = gen_golden_env.sim_cases()[name](modules, focus_cls)
+    gen_golden_env._seed_initializer(env, 2024)
+    got = gen_golden_env._rollout(env, actions, vector)
+    for key in ("obs0", "obs", "rew", "term", "trunc"):
+        assert got[key].dtype == gold[key].dtype, (key, got[key].dtype, gold[key].dtype)
+        numpy.testing.assert_array_equal(got[key], gold[key], err_msg=key)
+    assert gold["trunc"].any(), "the scenario should exercise episode ends"
+
+
+def test_spaces_follow_gymnasium_conventions(modules):
+    spaces = gym_compat.spaces
+    box = spaces.Box(numpy.float64(1.5), numpy.float64(2.5), dtype=numpy.float32)
+    assert box.shape == (1,) and box.dtype == numpy.float32  # scalar bounds -> shape (1,)
+    batched = gym_compat.batch_space(box, 4)
+    assert batched.shape == (4, 1) and batched.low.dtype == numpy.float32
+    assert numpy.all(batched.low == 1.5) and numpy.all(batched.high == 2.5)
+    discrete = spaces.Discrete(13)
+    assert gym_compat.batch_space(discrete, 3).shape == (3,)
+    assert discrete.contains(12) and not discrete.contains(13)
+    observer = modules.state_observer.IndexedElementObserver(5, 1, 5.0, 10.0)
+    assert observer.observation_space.shape == (5, 1)
+    assert observer.single_observation_space.shape == (1,)
+
+
+def test_histories_ring_buffer():
+    h = histories.Histories(3, 4)
+    assert numpy.isnan(h.data).all()
+    h.append_events([1.0, 2.0, 3.0])
+    h.append_events([4.0, 5.0], numpy.array([True, False, True]))
+    numpy.testing.assert_array_equal(h.most_recent_events(), [4.0, 2.0, 5.0])
+    numpy.testing.assert_array_equal(h.get_history(0), [1.0, 4.0])
+    numpy.testing.assert_array_equal(h.get_history(1), [2.0])
+    h.reset([False, True, False])
+    assert len(h.get_history(1)) == 0 and len(h.get_history(2)) == 2
+    for value in range(10):
+        h.append_events([value, value, value])
+    numpy.testing.assert_array_equal(h.get_history(0), [6.0, 7.0, 8.0, 9.0])
+
+
+def test_registry_builds_example_envs_lazily():
+    """examples/__init__.py registers the env ids; building them needs the GPU, so only the
+    registration and entry-point resolution are checked here."""
+
+    import examples  # noqa: F401
+
+    if gym_compat.USING_REAL_GYMNASIUM:
+        pytest.skip("real gymnasium registry in use")
+    spec = gym_compat._registry["DiscreteSteps-v0"]
+    assert spec.max_episode_steps == 20
+    assert gym_compat._load_entry_point(spec.vector_entry_point).__name__ == "VectorDiscreteSteps"
+    assert gym_compat._load_entry_point(spec.entry_point).__name__ == "DiscreteSteps"

@@ -386,3 +386,66 @@ def test_frames_match_reference_numba_cuda_golden(torch, path):
         head = renderer.context.rng_export(0, 64)
         numpy.testing.assert_array_equal(
             numpy.stack([head["s0"], head["s1"]], axis=1), gold[f"states_head_{i}"])
+
+
+# ----------------------------------------- env sequences vs the reference on a B200 (a13, b)
+
+
+def _env_gold(name):
+    path = os.path.join(GOLDEN, f"gpu_env_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated yet (oracle/gen_golden_env.py gpu)")
+    return numpy.load(path)
+
+
+def _compare_rollout(got, gold):
+    for key in ("term", "trunc"):
+        numpy.testing.assert_array_equal(got[key], gold[key], err_msg=key)
+    # observations / rewards are float32 functions of float64 focus values; ours is the
+    # exactly rounded variance while numpy.var() may sit an ulp off, so allow one float32 ulp
+    for key in ("obs0", "obs", "rew"):
+        assert got[key].dtype == gold[key].dtype
+        numpy.testing.assert_allclose(got[key], gold[key], rtol=0, atol=2.5e-7, err_msg=key)
+    exact = numpy.mean(got["obs"] == gold["obs"])
+    assert exact > 0.999, f"only {exact:.4%} of observations are bit-identical"
+
+
+def test_vector_discrete_steps_sequences_match_reference(torch):
+    """DiscreteSteps-v0 vector env, 8 envs, 50 steps with auto-resets: observations, rewards,
+    terminations and truncations against the reference's numba-CUDA run on a B200."""
+
+    from examples import custom_environments
+    from oracle import gen_golden_env
+
+    gold = _env_gold("vector_discrete_steps")
+    env = custom_environments.VectorDiscreteSteps(max_episode_steps=20, num_envs=8)
+    focus = env._observer._observers[0]._observers[1].single_observation_space
+    numpy.testing.assert_allclose(focus.low, gold["obs_low"], rtol=1e-6)
+    numpy.testing.assert_allclose(focus.high, gold["obs_high"], rtol=1e-6)
+    gen_golden_env._seed_initializer(env, 77)
+    got = gen_golden_env._rollout(env, gold["actions"], True)
+    assert gold["trunc"].any()
+    _compare_rollout(got, gold)
+
+
+def test_discrete_steps_sequences_match_reference(torch):
+    from examples import custom_environments
+    from oracle import gen_golden_env
+
+    gold = _env_gold("discrete_steps")
+    env = custom_environments.DiscreteSteps()
+    gen_golden_env._seed_initializer(env, 78)
+    got = gen_golden_env._rollout(env, gold["actions"], False)
+    _compare_rollout(got, gold)
+
+
+def test_registry_makes_the_example_envs(torch):
+    import examples  # noqa: F401
+    from reinfocus_b200 import gym_compat
+
+    env = gym_compat.make_vec("DiscreteSteps-v0", num_envs=3, vectorization_mode="custom")
+    obs, _ = env.reset()
+    assert obs.shape == (3, 4) and obs.dtype == numpy.float32
+    obs, rew, term, trunc, _ = env.step(numpy.array([6, 0, 12]))
+    assert obs.shape == (3, 4) and rew.shape == (3,) and not term.any()
+    assert numpy.all(numpy.abs(obs) <= 1)

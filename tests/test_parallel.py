@@ -1,0 +1,72 @@
+"""The multi-GPU path on CPU: env sharding arithmetic and the observation all-gather, run
+as a real 2-process torch.distributed job over gloo (rendezvous on 127.0.0.1)."""
+
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+from reinfocus_b200 import parallel
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("n,world", [(4096, 1), (4096, 2), (4096, 8), (13, 4), (5, 8), (0, 3)])
+def test_shard_bounds_partition_the_envs(n, world):
+    bounds = [parallel.shard_bounds(n, world, r) for r in range(world)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == n
+    for (_, last), (first, _) in zip(bounds, bounds[1:]):
+        assert last == first
+    sizes = [last - first for first, last in bounds]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+WORKER = textwrap.dedent("""
+    import sys
+    sys.path.insert(0, {repo!r})
+    import torch
+    import torch.distributed as dist
+    from reinfocus_b200 import parallel
+
+    rank, world, _ = parallel.init_from_env("gloo")
+    assert world == 2 and dist.get_backend() == "gloo"
+    for num_envs in (8, 7):
+        first, last = parallel.shard_bounds(num_envs, world, rank)
+        # each rank "observes" its own envs: value = global env index (+ column offset)
+        local = torch.arange(first, last, dtype=torch.float64)[:, None] + torch.tensor([[0.0, 0.5]])
+        gathered = parallel.gather_observations(local, num_envs)
+        want = torch.arange(num_envs, dtype=torch.float64)[:, None] + torch.tensor([[0.0, 0.5]])
+        assert gathered.shape == want.shape and torch.equal(gathered, want), (rank, gathered)
+    # max-over-ranks timing reduction used by bench.py
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert t.item() == 2.0
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_observation_gather_over_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(repo=REPO))
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for rank, proc in enumerate(procs):
+        out, _ = proc.communicate(timeout=180)
+        assert proc.returncode == 0, out
+        assert f"rank {rank} ok" in out
