@@ -102,16 +102,19 @@ def cpu_baseline(steps, warmup, cores_hint=None):
 
     import oracle
 
-    cores = oracle.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1: size the thread pool from the CPUs this process may
+    # use, not from the OpenMP default
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
     sample_envs = int(min(512, max(16, 8 * cores)))
     targets, planes = synthetic_inputs(sample_envs, steps + warmup)
+    oracle.lib().rfo_set_threads(cores)
     states = oracle.rng_states(sample_envs * HEIGHT * HEIGHT, 0, doubling=True)
     times = []
     for i in range(steps + warmup):
         t0 = time.perf_counter()
         world = oracle.pack_world(targets[i])
         cam = oracle.pack_cameras(planes[i])
-        oracle.step(world, cam, HEIGHT, SPP, states, profile=oracle.PROFILE_GPU)
+        oracle.step(world, cam, HEIGHT, SPP, states, profile=oracle.PROFILE_GPU, threads=cores)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)

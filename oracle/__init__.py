@@ -68,6 +68,7 @@ def lib() -> ctypes.CDLL:
             ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
         ]
         _lib.rfo_max_threads.restype = ctypes.c_int
+        _lib.rfo_set_threads.argtypes = [ctypes.c_int]
     return _lib
 
 
