@@ -159,13 +159,15 @@ int rf_step_device(rf_ctx *ctx, int n, int H, int spp, double *d_focus, void *st
  *                           float32 in [2^-60, 2^60]. */
 enum { RF_SELFTEST_CHECKER = 0, RF_SELFTEST_PIXEL_DIV = 1, RF_SELFTEST_INV_LENGTH = 2 };
 int rf_selftest(rf_ctx *ctx, int which, int arg, int64_t *mismatches, void *stream);
-/* Options. RF_OPT_FORCE_GENERIC = 1 makes rf_render use the literal any-camera kernel even
- * when the specialised default-camera kernel applies (A/B parity tests). */
+/* Options. RF_OPT_FORCE_GENERIC = 1 makes rf_render use the literal any-camera kernel and
+ * rf_focus the general staged kernel even when the specialised ones apply (A/B parity
+ * tests). */
 enum { RF_OPT_FORCE_GENERIC = 0 };
 int rf_set_option(rf_ctx *ctx, int option, int value);
 /* Introspection. RF_INFO_LAST_TRACE_KERNEL: 1 if the last rf_render used the specialised
- * kernel, 0 for the generic one, -1 before any render. */
-enum { RF_INFO_LAST_TRACE_KERNEL = 0 };
+ * kernel, 0 for the generic one, -1 before any render. RF_INFO_LAST_FOCUS_KERNEL: 1 if the
+ * last rf_focus used the packed kernel, 0 for the staged one. */
+enum { RF_INFO_LAST_TRACE_KERNEL = 0, RF_INFO_LAST_FOCUS_KERNEL = 1 };
 int rf_get_info(const rf_ctx *ctx, int what);
 /* Measures the FP32 FFMA peak of this GPU (dependent-chain-free FFMA loop on all SMs);
  * returns TFLOP/s counting 2 flop per FFMA. */

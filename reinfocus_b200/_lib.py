@@ -24,6 +24,7 @@ ABI_VERSION = 2
 SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH = 0, 1, 2
 OPT_FORCE_GENERIC = 0
 INFO_LAST_TRACE_KERNEL = 0
+INFO_LAST_FOCUS_KERNEL = 1
 
 STATE_DTYPE = numpy.dtype([("s0", numpy.uint64), ("s1", numpy.uint64)], align=True)
 
@@ -263,6 +264,9 @@ class Context:
 
     def last_trace_kernel(self) -> int:
         return int(self._lib.rf_get_info(self._handle, INFO_LAST_TRACE_KERNEL))
+
+    def last_focus_kernel(self) -> int:
+        return int(self._lib.rf_get_info(self._handle, INFO_LAST_FOCUS_KERNEL))
 
     def measure_fp32_peak(self) -> tuple[float, float]:
         tflops, mhz = ctypes.c_double(), ctypes.c_double()

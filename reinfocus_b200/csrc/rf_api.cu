@@ -58,6 +58,7 @@ struct rf_ctx {
 
     bool force_generic = false;  // RF_OPT_FORCE_GENERIC
     int last_kernel = -1;        // 0 generic, 1 fast (introspection for tests)
+    int last_focus_kernel = -1;  // 0 staged (general), 1 packed
 };
 
 namespace {
@@ -185,9 +186,49 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
     return RF_OK;
 }
 
+int launch_focus_packed(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, int channels,
+                        double *d_out, cudaStream_t stream) {
+    rf::PackedFocusParams p{};
+    p.accum = ctx->d_accum;
+    p.tickets = ctx->d_tickets;
+    p.H = H;
+    p.W = W;
+    p.channels = channels;
+    p.segs = (W + rf::kPackedCols - 1) / rf::kPackedCols;
+    // rows per warp tile: 4 halo rows are recomputed per tile, so prefer tall tiles, but
+    // keep at least ~4 warps per SM sub-partition in flight for small batches
+    const int64_t want_tiles = (int64_t)ctx->prop.multiProcessorCount * 32;
+    int band = 32;
+    while (band > 4 && (int64_t)n * p.segs * ((H + band - 1) / band) < want_tiles) band /= 2;
+    p.band = band;
+    p.bands = (H + band - 1) / band;
+    const int tiles = p.segs * p.bands;
+    const unsigned blocks_x = (unsigned)((tiles + rf::kPackedWarps - 1) / rf::kPackedWarps);
+    for (int first = 0; first < n; first += 65535) {
+        const int cnt = std::min(65535, n - first);
+        p.img = d_img + (int64_t)first * H * W * channels;
+        p.out = d_out + first;
+        p.accum = ctx->d_accum + 2 * (int64_t)first;
+        p.tickets = ctx->d_tickets + first;
+        p.n = cnt;
+        const dim3 grid(blocks_x, cnt);
+        if (channels == 1)
+            rf::focus_packed_kernel<1><<<grid, rf::kPackedWarps * 32, 0, stream>>>(p);
+        else
+            rf::focus_packed_kernel<3><<<grid, rf::kPackedWarps * 32, 0, stream>>>(p);
+        ctx->launches++;
+    }
+    RF_CUDA(ctx, cudaGetLastError());
+    return RF_OK;
+}
+
 int launch_focus(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, int channels,
                  double *d_out, uint8_t *d_median, uint8_t *d_laplacian, cudaStream_t stream) {
     if (int rc = ensure_focus_scratch(ctx, n, stream)) return rc;
+    const bool packed = !ctx->force_generic && !d_median && !d_laplacian && W % 4 == 0 && W >= 8 &&
+                        H >= 2 && (reinterpret_cast<uintptr_t>(d_img) & 3) == 0;
+    ctx->last_focus_kernel = packed ? 1 : 0;
+    if (packed) return launch_focus_packed(ctx, n, H, W, d_img, channels, d_out, stream);
     rf::FocusParams p{};
     p.img = d_img;
     p.out = d_out;
@@ -213,24 +254,18 @@ int launch_focus(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, int cha
     if (smem > 48 * 1024)
         RF_CUDA(ctx, cudaFuncSetAttribute(rf::focus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
-    const dim3 grid((H + rows - 1) / rows, n);
-    if (n > 65535) {
-        // gridDim.y limit: split the batch
-        for (int first = 0; first < n; first += 65535) {
-            const int cnt = std::min(65535, n - first);
-            rf::FocusParams q = p;
-            q.img = d_img + (int64_t)first * H * W * channels;
-            q.out = d_out + first;
-            q.median = d_median ? d_median + (int64_t)first * H * W : nullptr;
-            q.laplacian = d_laplacian ? d_laplacian + (int64_t)first * H * W : nullptr;
-            q.accum = ctx->d_accum + 2 * (int64_t)first;
-            q.tickets = ctx->d_tickets + first;
-            q.n = cnt;
-            rf::focus_kernel<<<dim3(grid.x, cnt), rf::kFocusThreads, smem, stream>>>(q);
-            ctx->launches++;
-        }
-    } else {
-        rf::focus_kernel<<<grid, rf::kFocusThreads, smem, stream>>>(p);
+    const unsigned bands = (unsigned)((H + rows - 1) / rows);
+    for (int first = 0; first < n; first += 65535) {
+        const int cnt = std::min(65535, n - first);
+        rf::FocusParams q = p;
+        q.img = d_img + (int64_t)first * H * W * channels;
+        q.out = d_out + first;
+        q.median = d_median ? d_median + (int64_t)first * H * W : nullptr;
+        q.laplacian = d_laplacian ? d_laplacian + (int64_t)first * H * W : nullptr;
+        q.accum = ctx->d_accum + 2 * (int64_t)first;
+        q.tickets = ctx->d_tickets + first;
+        q.n = cnt;
+        rf::focus_kernel<<<dim3(bands, cnt), rf::kFocusThreads, smem, stream>>>(q);
         ctx->launches++;
     }
     RF_CUDA(ctx, cudaGetLastError());
@@ -559,6 +594,8 @@ int rf_get_info(const rf_ctx *ctx, int what) {
     switch (what) {
         case RF_INFO_LAST_TRACE_KERNEL:
             return ctx->last_kernel;
+        case RF_INFO_LAST_FOCUS_KERNEL:
+            return ctx->last_focus_kernel;
         default:
             return -1;
     }

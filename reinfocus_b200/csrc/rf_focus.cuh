@@ -55,6 +55,28 @@ __device__ __forceinline__ void sort3(uint32_t &a, uint32_t &b, uint32_t &c) {
     c = hi;
 }
 
+// var = (N*S2 - S*S) / N^2 with an exact 128-bit numerator, one float64 division
+__device__ __forceinline__ double exact_variance(unsigned long long S, unsigned long long S2,
+                                                 unsigned long long N) {
+    const unsigned long long a_lo = N * S2, a_hi = __umul64hi(N, S2);
+    const unsigned long long b_lo = S * S, b_hi = __umul64hi(S, S);
+    const unsigned long long d_lo = a_lo - b_lo;
+    const unsigned long long d_hi = a_hi - b_hi - (a_lo < b_lo ? 1ull : 0ull);
+    // numerator -> float64, round-to-nearest-even from 128 bits
+    double num;
+    if (d_hi == 0) {
+        num = __ull2double_rn(d_lo);
+    } else {
+        // keep 64 significant bits with a sticky bit, then scale
+        const int lz = __clzll((long long)d_hi);
+        const unsigned long long top = lz ? ((d_hi << lz) | (d_lo >> (64 - lz))) : d_hi;
+        const unsigned long long rest = lz ? (d_lo << lz) : d_lo;
+        num = __ull2double_rn(top | (rest ? 1ull : 0ull)) * exp2((double)(64 - lz));
+    }
+    const double Nd = (double)N;
+    return __ddiv_rn(num, __dmul_rn(Nd, Nd));
+}
+
 __global__ void __launch_bounds__(kFocusThreads) focus_kernel(const FocusParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int e = blockIdx.y;
@@ -162,26 +184,167 @@ __global__ void __launch_bounds__(kFocusThreads) focus_kernel(const FocusParams 
             const unsigned long long S = atomicExch(&p.accum[2 * e], 0ull);
             const unsigned long long S2 = atomicExch(&p.accum[2 * e + 1], 0ull);
             p.tickets[e] = 0;
-            // var = (N*S2 - S*S) / N^2 with an exact 128-bit numerator
-            const unsigned long long N = (unsigned long long)H * (unsigned long long)W;
-            const unsigned long long a_lo = N * S2, a_hi = __umul64hi(N, S2);
-            const unsigned long long b_lo = S * S, b_hi = __umul64hi(S, S);
-            const unsigned long long d_lo = a_lo - b_lo;
-            const unsigned long long d_hi = a_hi - b_hi - (a_lo < b_lo ? 1ull : 0ull);
-            // numerator -> float64, round-to-nearest-even from 128 bits
-            double num;
-            if (d_hi == 0) {
-                num = __ull2double_rn(d_lo);
-            } else {
-                // keep 64 significant bits with a sticky bit, then scale
-                const int lz = __clzll((long long)d_hi);
-                const unsigned long long top =
-                    lz ? ((d_hi << lz) | (d_lo >> (64 - lz))) : d_hi;
-                const unsigned long long rest = lz ? (d_lo << lz) : d_lo;
-                num = __ull2double_rn(top | (rest ? 1ull : 0ull)) * exp2((double)(64 - lz));
+            p.out[e] = exact_variance(S, S2, (unsigned long long)H * (unsigned long long)W);
+        }
+    }
+}
+
+// =========================================================================================
+// Packed variant (the one the step path uses): no shared memory, no block barrier.
+//
+// A warp owns a tile of 120 x `band` output pixels of one env and marches down its rows.
+// Lane l holds four horizontally adjacent pixels (one 32-bit gray word) at columns
+// x0 = seg*120 - 4 + 4*l; lanes 0 and 31 are halo lanes whose medians feed the Laplacian of
+// their neighbours. All pixel arithmetic runs two pixels per instruction on zero-extended
+// u16x2 lanes with the native 3-input min/max (VIMNMX3.U16x2):
+//   column pass   lo/mid/hi of each vertical triple (mid = sum - lo - hi)
+//   row pass      median9 = med3(max3(lo's), med3(mid's), min3(hi's))
+//   Laplacian     N+S+E+W+1020-4C >= 0 per lane, clamp to [1020, 1275], subtract 1020
+//   sums          IDP.4A on the four packed 8-bit Laplacians
+// Horizontal neighbours come from the adjacent lanes by shuffle, vertical ones from the two
+// previous rows kept in registers. Borders: replicated gray (median), reflect-101 medians
+// (Laplacian), exactly as the staged kernel above. Requires W % 4 == 0, W >= 8, H >= 2 and a
+// 4-byte aligned image; anything else (and the debug planes) uses focus_kernel.
+// =========================================================================================
+
+constexpr int kPackedWarps = 8;
+constexpr int kPackedCols = 120;  // productive columns per warp tile
+
+struct PackedFocusParams {
+    const uint8_t *img;  // [n, H, W, channels]
+    double *out;
+    unsigned long long *accum;
+    unsigned int *tickets;
+    int n, H, W, channels;
+    int band;         // output rows per tile
+    int segs, bands;  // tiles per env = segs * bands
+};
+
+__device__ __forceinline__ uint32_t min3x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+__device__ __forceinline__ uint32_t max3x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+// per-lane median of three: sum - min - max (16-bit lanes never overflow: 3 * 255)
+__device__ __forceinline__ uint32_t med3x2(uint32_t a, uint32_t b, uint32_t c) {
+    return a + b + c - min3x2(a, b, c) - max3x2(a, b, c);
+}
+
+template <int kChannels>
+__device__ __forceinline__ uint32_t load_gray_word(const uint8_t *row, int x, int W) {
+    // four gray pixels x..x+3 of one image row, replicated outside [0, W)
+    if (x < 0) {
+        const uint32_t g = kChannels == 1
+                               ? row[0]
+                               : (9798u * row[0] + 19235u * row[1] + 3735u * row[2] + 16384u) >> 15;
+        return g * 0x01010101u;
+    }
+    if (x >= W) {
+        const uint8_t *px = row + (size_t)(W - 1) * kChannels;
+        const uint32_t g = kChannels == 1
+                               ? px[0]
+                               : (9798u * px[0] + 19235u * px[1] + 3735u * px[2] + 16384u) >> 15;
+        return g * 0x01010101u;
+    }
+    if (kChannels == 1) return __ldg(reinterpret_cast<const uint32_t *>(row + x));
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(row + (size_t)x * 3);
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    // bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+    const uint32_t g0 = (9798u * (w0 & 255u) + 19235u * ((w0 >> 8) & 255u) + 3735u * ((w0 >> 16) & 255u) + 16384u) >> 15;
+    const uint32_t g1 = (9798u * (w0 >> 24) + 19235u * (w1 & 255u) + 3735u * ((w1 >> 8) & 255u) + 16384u) >> 15;
+    const uint32_t g2 = (9798u * ((w1 >> 16) & 255u) + 19235u * (w1 >> 24) + 3735u * (w2 & 255u) + 16384u) >> 15;
+    const uint32_t g3 = (9798u * ((w2 >> 8) & 255u) + 19235u * ((w2 >> 16) & 255u) + 3735u * (w2 >> 24) + 16384u) >> 15;
+    return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+}
+
+template <int kChannels>
+__global__ void __launch_bounds__(kPackedWarps * 32) focus_packed_kernel(const PackedFocusParams p) {
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * kPackedWarps + (threadIdx.x >> 5);
+    const int tiles_per_env = p.segs * p.bands;
+    const int e = blockIdx.y;
+    if (tile >= tiles_per_env) return;  // whole warp
+    const int seg = tile % p.segs, band = tile / p.segs;
+    const int H = p.H, W = p.W;
+    const int y0 = band * p.band, y1 = min(y0 + p.band, H);
+    const int x0 = seg * kPackedCols - 4 + 4 * lane;
+    // this lane's four Laplacians count iff it is a productive lane inside the image
+    const bool counts = lane >= 1 && lane <= 30 && x0 < W;
+    const bool at_left = x0 == 0, at_right = x0 + 4 == W;
+
+    const uint8_t *img = p.img + (size_t)e * H * W * kChannels;
+    const size_t pitch = (size_t)W * kChannels;
+
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;  // packs of row r-2
+    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0;  // packs of row r-1
+    uint32_t m2a = 0, m2b = 0, m1a = 0, m1b = 0;      // medians of rows r-3 and r-2
+    uint32_t sum = 0, sum2 = 0;
+    const uint32_t bias = 1020u | (1020u << 16), top = 1275u | (1275u << 16);
+
+    for (int r = y0 - 2; r <= y1 + 1; ++r) {
+        const int ry = min(max(r, 0), H - 1);
+        const uint32_t g = load_gray_word<kChannels>(img + ry * pitch, x0, W);
+        const uint32_t gl = __shfl_up_sync(0xffffffffu, g, 1);
+        const uint32_t gr = __shfl_down_sync(0xffffffffu, g, 1);
+        // zero-extended column pairs (x0-1,x0) (x0,x0+1) (x0+1,x0+2) (x0+2,x0+3) (x0+3,x0+4)
+        const uint32_t lz = gl >> 24, rz = gr & 255u;
+        const uint32_t c0 = __byte_perm(lz, g, 0x2410);
+        const uint32_t c1 = __byte_perm(g, 0u, 0x4140);
+        const uint32_t c2 = __byte_perm(g, 0u, 0x4241);
+        const uint32_t c3 = __byte_perm(g, 0u, 0x4342);
+        const uint32_t c4 = __byte_perm(rz, g, 0x2017);
+        if (r >= y0) {
+            // column pass on rows r-2, r-1, r
+            const uint32_t lo0 = min3x2(a0, b0, c0), hi0 = max3x2(a0, b0, c0), md0 = a0 + b0 + c0 - lo0 - hi0;
+            const uint32_t lo1 = min3x2(a1, b1, c1), hi1 = max3x2(a1, b1, c1), md1 = a1 + b1 + c1 - lo1 - hi1;
+            const uint32_t lo2 = min3x2(a2, b2, c2), hi2 = max3x2(a2, b2, c2), md2 = a2 + b2 + c2 - lo2 - hi2;
+            const uint32_t lo3 = min3x2(a3, b3, c3), hi3 = max3x2(a3, b3, c3), md3 = a3 + b3 + c3 - lo3 - hi3;
+            const uint32_t lo4 = min3x2(a4, b4, c4), hi4 = max3x2(a4, b4, c4), md4 = a4 + b4 + c4 - lo4 - hi4;
+            // row pass: medians of row r-1 for pixels (x0, x0+1) and (x0+2, x0+3)
+            const uint32_t ma = med3x2(max3x2(lo0, lo1, lo2), med3x2(md0, md1, md2), min3x2(hi0, hi1, hi2));
+            const uint32_t mb = med3x2(max3x2(lo2, lo3, lo4), med3x2(md2, md3, md4), min3x2(hi2, hi3, hi4));
+            if (r >= y0 + 2) {
+                // Laplacian of row y = r-2: centre m1, up m2 (row r-3), down m (row r-1);
+                // reflect-101 at the top / bottom image rows
+                const int y = r - 2;
+                const uint32_t ua = y == 0 ? ma : m2a, ub = y == 0 ? mb : m2b;
+                const uint32_t da = y == H - 1 ? m2a : ma, db = y == H - 1 ? m2b : mb;
+                const uint32_t nl = __shfl_up_sync(0xffffffffu, m1b, 1);
+                const uint32_t nr = __shfl_down_sync(0xffffffffu, m1a, 1);
+                const uint32_t mid = __byte_perm(m1a, m1b, 0x5432);  // (m1, m2)
+                // (m-1, m0) and (m3, m4); at the image edges m-1 := m1 and m4 := m2
+                const uint32_t la = at_left ? __byte_perm(m1a, m1a, 0x1032) : __byte_perm(nl, m1a, 0x5432);
+                const uint32_t rb = at_right ? __byte_perm(m1b, m1b, 0x1032) : __byte_perm(m1b, nr, 0x5432);
+                uint32_t va = ua + da + la;
+                va = va + mid + bias - 4u * m1a;
+                uint32_t vb = ub + db + mid;
+                vb = vb + rb + bias - 4u * m1b;
+                va = min3x2(max3x2(va, bias, bias), top, top) - bias;
+                vb = min3x2(max3x2(vb, bias, bias), top, top) - bias;
+                uint32_t l4 = __byte_perm(va, vb, 0x6420);
+                l4 = counts ? l4 : 0u;
+                sum = __dp4a(l4, 0x01010101u, sum);
+                sum2 = __dp4a(l4, l4, sum2);
             }
-            const double Nd = (double)N;
-            p.out[e] = __ddiv_rn(num, __dmul_rn(Nd, Nd));
+            m2a = m1a; m2b = m1b;
+            m1a = ma; m1b = mb;
+        }
+        a0 = b0; a1 = b1; a2 = b2; a3 = b3; a4 = b4;
+        b0 = c0; b1 = c1; b2 = c2; b3 = c3; b4 = c4;
+    }
+
+    for (int off = 16; off > 0; off >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, off);
+        sum2 += __shfl_down_sync(0xffffffffu, sum2, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&p.accum[2 * e], (unsigned long long)sum);
+        atomicAdd(&p.accum[2 * e + 1], (unsigned long long)sum2);
+        __threadfence();
+        const unsigned int ticket = atomicAdd(&p.tickets[e], 1u);
+        if (ticket == (unsigned)tiles_per_env - 1) {
+            __threadfence();
+            const unsigned long long S = atomicExch(&p.accum[2 * e], 0ull);
+            const unsigned long long S2 = atomicExch(&p.accum[2 * e + 1], 0ull);
+            p.tickets[e] = 0;
+            p.out[e] = exact_variance(S, S2, (unsigned long long)H * (unsigned long long)W);
         }
     }
 }

@@ -290,6 +290,46 @@ def test_focus_matches_oracle_and_cv2(torch, shape):
     numpy.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13)
 
 
+@pytest.mark.parametrize("shape", [(2, 8), (5, 8), (33, 12), (40, 116), (40, 120), (40, 124), (40, 128),
+                                   (37, 240), (64, 244), (31, 364), (300, 300), (75, 1200)])
+@pytest.mark.parametrize("channels", [1, 3])
+def test_packed_focus_kernel_equals_staged_kernel_and_oracle(torch, shape, channels):
+    """The warp-marching u16x2 kernel (W % 4 == 0) against the staged general kernel (A/B on
+    the device) and the oracle, gray and RGB input, widths around the 120-column tile."""
+
+    from reinfocus_b200 import _lib
+
+    rng = numpy.random.default_rng(shape[0] * 7919 + shape[1] + channels)
+    n = 3
+    base = numpy.linspace(0, 180, shape[1])[None, None, :, None] * numpy.linspace(0.3, 1, shape[0])[None, :, None, None]
+    imgs = (base + rng.integers(0, 76, size=(n,) + shape + (3,))).astype(numpy.uint8)
+    imgs[1, ::3] = 255  # saturating rows: exercises both clamps of the Laplacian
+    imgs[2, :, ::5] = 0
+    data = imgs if channels == 3 else oracle.gray(imgs)
+    want = oracle.focus_values(imgs) if channels == 3 else oracle.focus_values_gray(data)
+    dev = torch.from_numpy(data).cuda()
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    packed, staged = _lib.Context(), _lib.Context()
+    staged.set_option(_lib.OPT_FORCE_GENERIC, 1)
+    for context, kernel in ((packed, 1), (staged, 0)):
+        for _ in range(2):  # twice: the accumulators must be re-armed by the last tile
+            out.zero_()
+            context.focus(n, shape[0], shape[1], dev.data_ptr(), channels, out.data_ptr())
+            numpy.testing.assert_array_equal(out.cpu().numpy(), want)
+        assert context.last_focus_kernel() == kernel
+
+
+def test_packed_focus_kernel_on_a_large_batch(torch):
+    """4096-env-like launch shape at reduced height: many envs, grid.y > tiles."""
+
+    from reinfocus_b200 import vision
+
+    rng = numpy.random.default_rng(11)
+    gray = rng.integers(0, 256, size=(700, 36, 300), dtype=numpy.uint8)
+    got = vision.focus_values_device(torch.from_numpy(gray).cuda()).cpu().numpy()
+    numpy.testing.assert_array_equal(got, oracle.focus_values_gray(gray))
+
+
 def test_focus_planes_match_oracle(ctx, torch):
     rng = numpy.random.default_rng(3)
     gray = rng.integers(0, 256, size=(4, 37, 53), dtype=numpy.uint8)
