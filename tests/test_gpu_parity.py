@@ -241,6 +241,23 @@ def test_gray_output_is_cv2_gray_of_rgb(torch):
     numpy.testing.assert_array_equal(gray, oracle.gray(rgb))
 
 
+@pytest.mark.parametrize("height", [8, 44, 48, 100])
+def test_gray_only_render_equals_oracle(torch, height):
+    """Gray-only renders (the step path's output) at several sizes: the pixels, and the states
+    they leave behind, are the oracle's."""
+
+    spp = 7
+    gpu = _renderer(samples_per_pixel=spp)
+    cpu = oracle.OracleFastRenderer(samples_per_pixel=spp, profile=oracle.PROFILE_GPU)
+    for renderer in (gpu, cpu):
+        renderer.update_targets([6.5, 9.0, 5.0])
+        renderer.update_focus_planes([6.0, 9.0, 10.0])
+    for _ in range(2):
+        gray = gpu.render_gray_device(height).cpu().numpy()
+        numpy.testing.assert_array_equal(gray, oracle.gray(cpu.render(height)))
+    numpy.testing.assert_array_equal(gpu.context.rng_export(), cpu.states)
+
+
 def test_batch_split_property_at_64_envs(torch):
     """Size-independent property: rendering a batch equals rendering each env alone with
     that env's slice of the RNG states (env e owns states [e*H*W, (e+1)*H*W))."""
