@@ -256,6 +256,17 @@ def run_ours(args):
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = {}
+    try:
+        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f)
+    except OSError:
+        pass
+
+    def scaled_traffic(key):
+        per_env = traffic.get(key)
+        return per_env * n_local if per_env else None
+
     focus_bytes = n_local * HEIGHT * HEIGHT + 8 * n_local
     base = cpu_baseline(max(1, min(args.steps, 2)), 1) if not args.no_cpu_baseline else None
 
@@ -281,7 +292,10 @@ def run_ours(args):
         "roofline": {
             "kernel": "rf::trace_kernel", "bound": "fp32",
             "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-            "frac": achieved_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+            "frac": achieved_tflops / fp32_peak if fp32_peak else None,
+            "traffic": scaled_traffic("trace_kernel_bytes_per_env"),
+            "traffic_source": "ncu dram bytes per env at 256 envs (profiles/ncu_traffic.json) x envs per launch",
+            "algorithmic_bytes_per_launch": n_local * HEIGHT * HEIGHT * 33,
             "peak_source": f"FFMA loop measured live on this GPU (implies {implied_mhz:.0f} MHz); "
                            f"theoretical 148 SM x 128 x 2 x 1.965 GHz = {THEORETICAL_FP32_TFLOPS:.1f}",
             "algorithmic_flop_per_ray": FLOP_PER_RAY, "rays_per_launch": rays_local,
@@ -290,7 +304,8 @@ def run_ours(args):
         "roofline_focus": {
             "kernel": "rf::focus_kernel", "bound": "hbm", "achieved": focus_bytes / (focus_ms * 1e-3) / 1e9,
             "peak": hbm_peak, "unit": "GB/s",
-            "frac": focus_bytes / (focus_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+            "frac": focus_bytes / (focus_ms * 1e-3) / 1e9 / hbm_peak,
+            "traffic": scaled_traffic("focus_kernel_bytes_per_env"),
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
             "launch_ms": focus_ms, "algorithmic_bytes_per_launch": focus_bytes,
         },

@@ -74,8 +74,12 @@ def launches(path):
 
 if __name__ == "__main__":
     src, dst = sys.argv[1], sys.argv[2]
-    parts = [launches(src + "_launches.csv"), summarise(src + "_trace.ncu-rep", "tracer, --set full"),
-             summarise(src + "_focus.ncu-rep", "focus stencil, --set full")]
+    import os
+
+    parts = [launches(src + "_launches.csv")]
+    for suffix, title in (("_trace.ncu-rep", "tracer, --set full"), ("_focus.ncu-rep", "focus stencil, --set full")):
+        if os.path.exists(src + suffix):
+            parts.append(summarise(src + suffix, title))
     with open(dst + "_ncu_summary.txt", "w") as f:
         f.write("\n\n".join(parts) + "\n")
     print("\n\n".join(parts))
