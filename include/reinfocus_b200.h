@@ -119,6 +119,25 @@ int rf_render(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint8_t
               void *stream);
 
 /* -------------------------------------------------------------------------------------
+ * General-scene tracer. Replaces reference graphics/render.py:88-119 (render) and :31-85
+ * (device_render): spheres and z-aligned rectangles with per-shape checker frequency, up to
+ * 50 bounces, one camera per env, fresh RNG states from `seed` on every call (the reference
+ * seeds 0, render.py:115). Host inputs, laid out as the reference's Worlds / Cameras build
+ * them (world.py:27-82, camera.py:59-91):
+ *   h_shape_params float32 [n, max_shapes, 7]  sphere: cx cy cz r fx fy 0
+ *                                              rectangle: xmin xmax ymin ymax z fx fy
+ *   h_shape_types  int32   [n, max_shapes]     0 sphere, 1 rectangle
+ *   h_env_sizes    int32   [n]                 shapes in use per env
+ *   h_cameras      float64 [n, 19]             lower-left, horizontal, vertical, origin, u, v
+ *                                              (3 each) and the lens radius
+ * Output d_rgb uint8 [n, H, W, 3]. Synchronous.
+ * ----------------------------------------------------------------------------------- */
+int rf_render_generic(rf_ctx *ctx, int n, int H, int W, int spp, int max_shapes,
+                      const float *h_shape_params, const int *h_shape_types,
+                      const int *h_env_sizes, const double *h_cameras, uint64_t seed,
+                      uint8_t *d_rgb, void *stream);
+
+/* -------------------------------------------------------------------------------------
  * Focus measure. Replaces reference vision.py:11-39 (focus_value / focus_values:
  * cv2.cvtColor -> cv2.medianBlur(3) -> cv2.Laplacian(CV_8U) -> ndarray.var()).
  * d_img is uint8 [n, H, W, channels] with channels 1 (gray) or 3 (RGB);

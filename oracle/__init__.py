@@ -53,6 +53,11 @@ def lib() -> ctypes.CDLL:
             ctypes.c_void_p, ctypes.c_void_p, c_float_p, c_float_p, c_float_p,
             ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
         ]
+        _lib.rfo_render_generic.argtypes = [
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_int,
+        ]
         _lib.rfo_gray.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
         _lib.rfo_focus_gray.argtypes = [
             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
@@ -194,6 +199,26 @@ def render_fast(world, cam_dyn, frame_height, spp, states, profile=PROFILE_GPU,
     lib().rfo_render_fast(profile, n, H, W, int(spp), world.ctypes.data, cam_dyn.ctypes.data,
                           _f3(origin), _f3(u), _f3(v), float(lens_radius),
                           states.ctypes.data, frames.ctypes.data, threads)
+    return frames
+
+
+def render_generic(shape_params, shape_types, env_sizes, cameras, frame_shape, spp, threads=0):
+    """reference render.render (render.py:88-119): fresh seed-0 states, general scenes."""
+
+    shape_params = numpy.ascontiguousarray(shape_params, dtype=numpy.float32)
+    if shape_params.shape[2] < 7:
+        shape_params = numpy.ascontiguousarray(
+            numpy.pad(shape_params, ((0, 0), (0, 0), (0, 7 - shape_params.shape[2]))))
+    shape_types = numpy.ascontiguousarray(shape_types, dtype=numpy.int32)
+    env_sizes = numpy.ascontiguousarray(env_sizes, dtype=numpy.int32)
+    cameras = numpy.ascontiguousarray(cameras, dtype=numpy.float64)
+    n, max_shapes, _ = shape_params.shape
+    H, W = int(frame_shape[0]), int(frame_shape[1])
+    states = rng_states(n * H * W, 0, doubling=True)
+    frames = numpy.empty((n, H, W, 3), dtype=numpy.uint8)
+    lib().rfo_render_generic(n, H, W, int(spp), max_shapes, shape_params.ctypes.data,
+                             shape_types.ctypes.data, env_sizes.ctypes.data, cameras.ctypes.data,
+                             states.ctypes.data, frames.ctypes.data, threads)
     return frames
 
 

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "rf_scene_envs": (ctypes.c_int, [_vp]),
     "rf_render": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                  _vp, _vp, _vp]),
+    "rf_render_generic": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_uint64, _vp, _vp]),
     "rf_focus": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
                                 ctypes.c_int, _vp, _vp]),
     "rf_focus_planes": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
@@ -233,6 +235,21 @@ class Context:
                d_gray: int | None, stream=None):
         self._check(self._lib.rf_render(self._handle, n, height, width, spp, _vp(d_rgb),
                                         _vp(d_gray), _stream_ptr(stream)))
+
+    def render_generic(self, shape_params: numpy.ndarray, shape_types: numpy.ndarray,
+                       env_sizes: numpy.ndarray, cameras: numpy.ndarray, height: int, width: int,
+                       spp: int, d_rgb: int, seed: int = 0, stream=None):
+        shape_params = numpy.ascontiguousarray(shape_params, dtype=numpy.float32)
+        shape_types = numpy.ascontiguousarray(shape_types, dtype=numpy.int32)
+        env_sizes = numpy.ascontiguousarray(env_sizes, dtype=numpy.int32)
+        cameras = numpy.ascontiguousarray(cameras, dtype=numpy.float64)
+        n, max_shapes, width_params = shape_params.shape
+        assert width_params == 7 and shape_types.shape == (n, max_shapes)
+        assert env_sizes.shape == (n,) and cameras.shape == (n, 19)
+        self._check(self._lib.rf_render_generic(
+            self._handle, n, height, width, spp, max_shapes, shape_params.ctypes.data,
+            shape_types.ctypes.data, env_sizes.ctypes.data, cameras.ctypes.data,
+            ctypes.c_uint64(seed & (2**64 - 1)), _vp(d_rgb), _stream_ptr(stream)))
 
     def focus(self, n: int, height: int, width: int, d_img: int, channels: int, d_out: int,
               d_median: int | None = None, d_laplacian: int | None = None, stream=None):

@@ -16,14 +16,14 @@ LIB_NAME = "libreinfocus_b200.so"
 LIB_PATH = os.path.join(PACKAGE_DIR, LIB_NAME)
 
 SOURCES = ["rf_api.cu"]
-HEADERS = ["rf_rng.cuh", "rf_tracer.cuh", "rf_focus.cuh"]
+HEADERS = ["rf_rng.cuh", "rf_tracer.cuh", "rf_focus.cuh", "rf_generic.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    # every FP op in the kernels is an explicit round-to-nearest intrinsic; keep nvcc from
-    # contracting anything that is not
-    "-fmad=false",
+    # every FP op of the reference arithmetic is an explicit round-to-nearest intrinsic, which
+    # nvcc never contracts; library math (the float64 sin of the general-scene tracer) keeps
+    # the default contraction so that it matches libdevice as numba links it
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
 ]

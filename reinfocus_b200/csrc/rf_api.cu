@@ -13,6 +13,7 @@
 
 #include "../../include/reinfocus_b200.h"
 #include "rf_focus.cuh"
+#include "rf_generic.cuh"
 #include "rf_rng.cuh"
 #include "rf_tracer.cuh"
 
@@ -509,6 +510,63 @@ int rf_render(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint8_t
     DeviceGuard guard(ctx->device);
     if (int rc = rf_rng_ensure(ctx, (int64_t)n * H * W, 0, stream)) return rc;
     return launch_trace(ctx, n, H, W, spp, d_rgb, d_gray, (cudaStream_t)stream);
+}
+
+int rf_render_generic(rf_ctx *ctx, int n, int H, int W, int spp, int max_shapes,
+                      const float *h_shape_params, const int *h_shape_types, const int *h_env_sizes,
+                      const double *h_cameras, uint64_t seed, uint8_t *d_rgb, void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_render_generic: ctx is NULL");
+    RF_REQUIRE(ctx, n > 0 && H > 0 && W > 0 && spp > 0 && max_shapes > 0,
+               "rf_render_generic: n, H, W, spp, max_shapes must be positive");
+    RF_REQUIRE(ctx, h_shape_params && h_shape_types && h_env_sizes && h_cameras && d_rgb,
+               "rf_render_generic: NULL buffer");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t total = (int64_t)n * H * W;
+    const size_t bytes_params = sizeof(float) * (size_t)n * max_shapes * rf::kShapeParams;
+    const size_t bytes_types = sizeof(int) * (size_t)n * max_shapes;
+    const size_t bytes_sizes = sizeof(int) * (size_t)n;
+    const size_t bytes_cams = sizeof(double) * (size_t)n * rf::kCameraFields;
+    // one scratch allocation: cameras | params | types | sizes | states (fresh every call,
+    // reference render.py:115)
+    const size_t off_params = bytes_cams;
+    const size_t off_types = off_params + bytes_params;
+    const size_t off_sizes = off_types + bytes_types;
+    const size_t off_states = (off_sizes + bytes_sizes + 15) & ~(size_t)15;
+    uint8_t *scratch = nullptr;
+    RF_CUDA(ctx, cudaMalloc((void **)&scratch, off_states + sizeof(rf::RngState) * (size_t)total));
+    auto release = [&](int code) {
+        cudaStreamSynchronize(s);
+        cudaFree(scratch);
+        return code;
+    };
+    if (cudaMemcpyAsync(scratch, h_cameras, bytes_cams, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(scratch + off_params, h_shape_params, bytes_params, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(scratch + off_types, h_shape_types, bytes_types, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(scratch + off_sizes, h_env_sizes, bytes_sizes, cudaMemcpyHostToDevice, s) != cudaSuccess)
+        return release(fail(ctx, RF_ERR_CUDA, "rf_render_generic: upload failed"));
+    rf::RngState *states = reinterpret_cast<rf::RngState *>(scratch + off_states);
+    if (int rc = rng_init_into(ctx, states, total, seed, s)) return release(rc);
+    rf::GenericParams p{};
+    p.cameras = reinterpret_cast<const double *>(scratch);
+    p.shape_params = reinterpret_cast<const float *>(scratch + off_params);
+    p.shape_types = reinterpret_cast<const int *>(scratch + off_types);
+    p.env_sizes = reinterpret_cast<const int *>(scratch + off_sizes);
+    p.states = states;
+    p.rgb = d_rgb;
+    p.scale = (float)(255.0 / (double)spp);
+    p.n = n;
+    p.H = H;
+    p.W = W;
+    p.spp = spp;
+    p.max_shapes = max_shapes;
+    p.total = total;
+    const int64_t blocks = (total + rf::kTraceThreads - 1) / rf::kTraceThreads;
+    if (blocks > 0x7fffffffLL) return release(fail(ctx, RF_ERR_INVALID, "render batch too large"));
+    rf::trace_generic_kernel<<<(unsigned)blocks, rf::kTraceThreads, 0, s>>>(p);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) return release(fail(ctx, RF_ERR_CUDA, "generic tracer launch failed"));
+    return release(RF_OK);
 }
 
 // -------------------------------------------------------------------------------- focus

@@ -13,6 +13,51 @@ from reinfocus_b200.graphics import device_data
 from reinfocus_b200.graphics import vector
 
 
+GpuCamera = tuple  # (lower_left, horizontal, vertical, origin, u, v, lens_radius)
+
+
+def make_gpu_camera(aperture: float = 0.1, aspect_ratio: float = 1, focus_distance: float = 10,
+                    look_at: vector.V3F = vector.v3f(0, 0, -10),
+                    look_from: vector.V3F = vector.v3f(0, 0, 0), up: vector.V3F = vector.v3f(0, 1, 0),
+                    vfov: float = 30) -> GpuCamera:
+    # pylint: disable=too-many-arguments
+    """A thin-lens camera for the general-scene tracer (reference camera.py:182-226); the same
+    float32 arithmetic as FastCameras, with a Python-float focus distance (so the scalar
+    products are float64 before they meet the float32 vectors)."""
+
+    half_height = math.tan((vfov * math.pi / 180.0) / 2.0)
+    half_width = aspect_ratio * half_height
+    w = vector.norm_v3f(vector.sub_v3f(look_from, look_at))
+    u = vector.norm_v3f(vector.cross_v3f(up, w))
+    v = vector.cross_v3f(w, u)
+    return (
+        vector.sub_v3f(look_from, vector.add_v3f((vector.smul_v3f(u, half_width * focus_distance),
+                                                  vector.smul_v3f(v, half_height * focus_distance),
+                                                  vector.smul_v3f(w, focus_distance)))),
+        vector.smul_v3f(u, 2.0 * half_width * focus_distance),
+        vector.smul_v3f(v, 2.0 * half_height * focus_distance),
+        look_from, u, v, numpy.divide(aperture, 2.0),
+    )
+
+
+class Cameras:
+    # pylint: disable=too-few-public-methods
+    """One camera per env as a float64 [n, 19] array: the six float32 vectors and the float64
+    lens radius side by side, which numpy.hstack promotes to float64 (reference
+    camera.py:59-91)."""
+
+    def __init__(self, *cameras: GpuCamera):
+        self._cameras = numpy.hstack(
+            [[cam[i] for cam in cameras] for i in range(6)]
+            + [numpy.reshape([cam[6] for cam in cameras], (len(cameras), 1))])
+
+    def __len__(self) -> int:
+        return len(self._cameras)
+
+    def device_data(self) -> NDArray[numpy.float64]:
+        return self._cameras
+
+
 class FastCameras(device_data.DeviceData):
     def __init__(self, aspect_ratio: float = 1, look_from: vector.V3F = vector.v3f(0, 0, 0),
                  look_at: vector.V3F = vector.v3f(0, 0, -10),

@@ -25,6 +25,30 @@ def make_render_target(frame_shape: tuple[int, ...] = (300, 600)):
     return torch.empty(tuple(frame_shape) + (3,), dtype=torch.uint8, device="cuda")
 
 
+def render(world_data: world.Worlds, cameras: camera.Cameras, frame_shape: tuple[int, int] = (300, 600),
+           block_shape: tuple[int, int, int] = (1, 16, 16),
+           samples_per_pixel: int = 100) -> NDArray[numpy.uint8]:
+    # pylint: disable=unused-argument
+    """Ray traced images uint8 (n, H, W, 3) of general scenes (spheres, rectangles, up to 50
+    bounces) seen by one camera per env (reference render.py:88-119). RNG states are created
+    from seed 0 on every call, as in the reference. ``block_shape`` is accepted for signature
+    compatibility."""
+
+    import torch
+
+    ctx = _lib.shared_context()
+    n = len(world_data)
+    assert len(cameras) >= n, "one camera per env is required"
+    height, width = frame_shape
+    frames = torch.empty((n, height, width, 3), dtype=torch.uint8, device=f"cuda:{ctx.device}")
+    parameters, types, sizes = world_data.device_data()
+    if parameters.shape[2] < 7:
+        parameters = numpy.pad(parameters, ((0, 0), (0, 0), (0, 7 - parameters.shape[2])))
+    ctx.render_generic(parameters, types, sizes, cameras.device_data()[:n], height, width,
+                       samples_per_pixel, frames.data_ptr(), seed=0)
+    return frames.cpu().numpy()
+
+
 class FastRenderer:
     """Produces images of focus scenes (reference render.py:122-257).
 

@@ -1,11 +1,39 @@
-"""Per-env target parameters (reference graphics/world.py:85-123 FastWorlds)."""
+"""Per-env scene parameters (reference graphics/world.py): FastWorlds for the env path, Worlds
+for the general-scene tracer."""
 
 import math
+from collections.abc import Collection
 
 import numpy
 from numpy.typing import NDArray
 
 from reinfocus_b200.graphics import device_data
+from reinfocus_b200.graphics import shape
+
+
+class Worlds:
+    """Sets of shapes, one set per env, padded to the largest set (reference world.py:27-82):
+    parameters float32 [n, S, P], types int32 [n, S], sizes int32 [n]."""
+
+    def __init__(self, *env_shapes: Collection[shape.CpuShape]):
+        self._num_envs = len(env_shapes)
+        self._sizes = numpy.array([len(shapes) for shapes in env_shapes], dtype=numpy.int32)
+        most = int(max(self._sizes))
+        width = max(max(len(s.parameters) for s in shapes) for shapes in env_shapes)
+        self._parameters = numpy.zeros((self._num_envs, most, width), dtype=numpy.float32)
+        self._types = numpy.zeros((self._num_envs, most), dtype=numpy.int32)
+        for env, shapes in enumerate(env_shapes):
+            for index, item in enumerate(shapes):
+                self._parameters[env, index, :len(item.parameters)] = item.parameters
+                self._types[env, index] = item.shape_type
+
+    def __len__(self) -> int:
+        return self._num_envs
+
+    def device_data(self):
+        """(parameters, types, sizes) as host arrays; render() uploads them."""
+
+        return self._parameters, self._types, self._sizes
 
 
 class FastWorlds(device_data.DeviceData):

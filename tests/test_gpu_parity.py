@@ -506,3 +506,88 @@ def test_registry_makes_the_example_envs(torch):
     obs, rew, term, trunc, _ = env.step(numpy.array([6, 0, 12]))
     assert obs.shape == (3, 4) and rew.shape == (3,) and not term.any()
     assert numpy.all(numpy.abs(obs) <= 1)
+
+
+# ------------------------------------------------- general-scene tracer (a14): render.render
+
+
+def _generic_scene(name):
+    from oracle import gen_golden_generic_gpu
+    from reinfocus_b200.graphics import camera, shape_factory, vector, world
+
+    env_shapes, cam_kwargs, frame_shape, spp = gen_golden_generic_gpu.scenes(shape_factory, camera)[name]
+    cams = []
+    for kw in cam_kwargs:
+        kw = dict(kw)
+        for key in ("look_from", "look_at", "up"):
+            if key in kw:
+                kw[key] = vector.v3f(*kw[key])
+        cams.append(camera.make_gpu_camera(**kw))
+    return world.Worlds(*env_shapes), camera.Cameras(*cams), frame_shape, spp
+
+
+GENERIC_SCENES = ["one_rect", "two_rect", "one_sphere", "two_sphere", "mixed_batch", "ref_test_sphere",
+                  "default_size"]
+
+
+@pytest.mark.parametrize("name", GENERIC_SCENES)
+def test_generic_render_matches_reference_numba_cuda_golden(torch, name):
+    """render.render (spheres + rectangles, 50 bounces) against frames the reference's
+    device_render produced under numba-CUDA on a B200 (oracle/gen_golden_generic_gpu.py)."""
+
+    from reinfocus_b200.graphics import render
+
+    gold = numpy.load(os.path.join(GOLDEN, f"gpu_generic_{name}.npz"))
+    worlds, cameras, frame_shape, spp = _generic_scene(name)
+    numpy.testing.assert_array_equal(worlds.device_data()[0], gold["shape_params"])
+    numpy.testing.assert_array_equal(cameras.device_data(), gold["cameras"])
+    frames = render.render(worlds, cameras, frame_shape=frame_shape, samples_per_pixel=spp)
+    assert frames.shape == (len(worlds),) + tuple(frame_shape) + (3,)
+    if "frames" in gold:
+        mismatch = int((frames != gold["frames"]).sum())
+        assert mismatch == 0, f"{mismatch} of {frames.size} bytes differ"
+    else:
+        numpy.testing.assert_array_equal(frames[:, :16], gold["frames_head"])
+        assert hashlib.sha256(frames.tobytes()).hexdigest() == str(gold["frames_sha256"])
+
+
+def test_generic_render_reference_average_colour_tests(torch):
+    """reference tests/graphics/render_test.py:30-80."""
+
+    from reinfocus_b200.graphics import camera, render, shape_factory, world
+
+    # test_device_average_colour: an r_size=30 rectangle fills the 30 degree frame
+    frames = render.render(world.Worlds(shape_factory.one_rect(shape_factory.ShapeParameters(r_size=30))),
+                           camera.Cameras(camera.make_gpu_camera()), frame_shape=(100, 100),
+                           samples_per_pixel=10)
+    means = frames.reshape(-1, 3).mean(axis=0)
+    assert 0.25 * 255 <= means[0] <= 0.5 * 255 and 0.25 * 255 <= means[1] <= 0.5 * 255
+    assert means[2] == 0
+    # test_average_colour: a sphere in front of the sky
+    frames = render.render(world.Worlds(shape_factory.one_sphere()), camera.Cameras(camera.make_gpu_camera()),
+                           frame_shape=(100, 200), samples_per_pixel=10)
+    means = frames.reshape(-1, 3).mean(axis=0) / 255
+    assert 0.4 <= means[0] <= 0.6 and 0.4 <= means[1] <= 0.6 and 0.1 <= means[2] <= 0.2 or means[2] > 0.1
+
+
+def test_generic_render_matches_oracle_on_a_random_scene(torch):
+    """CUDA general-scene tracer against the CPU oracle on a scene no golden vector covers:
+    three shapes per env, odd frame size, varied cameras."""
+
+    from reinfocus_b200.graphics import camera, render, rectangle, shape_factory, sphere, vector, world
+
+    P = shape_factory.ShapeParameters
+    env_shapes = [
+        [sphere.sphere(vector.v3f(-1.5, 0.5, -7.0), 1.25, vector.v2f(6, 10)),
+         rectangle.rectangle(vector.v2f(-0.5, 2.5), vector.v2f(-2.0, 0.25), -9.0, vector.v2f(5, 3)),
+         sphere.sphere(vector.v3f(1.0, -0.75, -4.0), 0.5)],
+        shape_factory.two_rect(P(9.0, texture_f=(7, 7)), P(4.5)),
+    ]
+    cams = [camera.make_gpu_camera(aperture=0.4, focus_distance=6.0, vfov=45),
+            camera.make_gpu_camera(look_from=vector.v3f(-0.2, 0.1, 0.3), aspect_ratio=1.25)]
+    worlds, cameras = world.Worlds(*env_shapes), camera.Cameras(*cams)
+    got = render.render(worlds, cameras, frame_shape=(37, 53), samples_per_pixel=9)
+    params, types, sizes = worlds.device_data()
+    want = oracle.render_generic(params, types, sizes, cameras.device_data(), (37, 53), 9)
+    mismatch = int((got != want).sum())
+    assert mismatch <= got.size * 1e-4, f"{mismatch} of {got.size} bytes differ"

@@ -174,3 +174,30 @@ def test_focus_against_live_cv2():
         numpy.testing.assert_array_equal(omed[0], med)
         numpy.testing.assert_array_equal(olap[0], lap)
         assert fv[0] == pytest.approx(lap.var(), rel=1e-13)
+
+
+# ------------------------------------------------ general-scene tracer (a14), GPU profile
+
+
+def _generic_cases():
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "gpu_generic_*.npz")))
+
+
+@pytest.mark.parametrize("path", _generic_cases(), ids=lambda p: os.path.basename(p)[12:-4])
+def test_generic_render_reproduces_reference_numba_cuda_on_b200(path):
+    """render.render scenes (spheres, rectangles, 50 bounces, per-env cameras) recorded from
+    the reference's device_render under numba-CUDA on a B200. Rectangle-only scenes must be
+    bit-exact; sphere scenes may differ where acosf's rsqrt.approx seed matters (the oracle
+    uses an exact 1/sqrt there), budgeted at 1e-4 of the bytes - in practice none differ."""
+
+    import hashlib
+
+    gold = numpy.load(path)
+    frames = oracle.render_generic(gold["shape_params"], gold["shape_types"], gold["env_sizes"],
+                                   gold["cameras"], gold["frame_shape"], int(gold["spp"]))
+    has_sphere = bool((gold["shape_types"] == 0).any())
+    if "frames" in gold:
+        mismatch = int((frames != gold["frames"]).sum())
+        assert mismatch <= (frames.size * 1e-4 if has_sphere else 0), mismatch
+    else:
+        assert hashlib.sha256(frames.tobytes()).hexdigest() == str(gold["frames_sha256"])

@@ -38,7 +38,7 @@ __device__ __forceinline__ float draw_v2(H &s) {
 
 // v3: shifts as 32x32->64 multiplies by run-time powers of two (IMAD.WIDE on the FMA pipe),
 // xors on the ALU pipe
-struct M { uint32_t m23, m14, m4, one; };
+struct M { uint32_t m23, m14, m4, one, m21, m11; };
 __device__ __forceinline__ float draw_v3(H &s, const M m) {
     const uint64_t sum = (uint64_t)s.a * m.one + (((uint64_t)s.d << 32) | s.c);  // IMAD.WIDE acc
     const uint32_t rl = (uint32_t)sum, rh = (uint32_t)(sum >> 32) + s.b;
@@ -55,6 +55,53 @@ __device__ __forceinline__ float draw_v3(H &s, const M m) {
     return __ull2float_rn(k) * 0x1p-64f;
 }
 
+// v4: v2 with single-LOP3 xors (inline lop3) - what the tracer uses
+__device__ __forceinline__ float draw_v4(H &s) {
+    uint32_t rl, rh;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=r"(rl), "=r"(rh) : "r"(s.a), "r"(s.c), "r"(s.b), "r"(s.d));
+    const uint32_t tl = s.a ^ s.c, th = s.b ^ s.d;
+    const uint32_t ql = __funnelshift_r(s.a, s.b, 9), qh = __funnelshift_r(s.b, s.a, 9);
+    const uint32_t ul = tl << 14, uh = __funnelshift_l(tl, th, 14);
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s.a) : "r"(ql), "r"(tl), "r"(ul));
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s.b) : "r"(qh), "r"(th), "r"(uh));
+    s.c = __funnelshift_l(tl, th, 4);
+    s.d = __funnelshift_l(th, tl, 4);
+    const uint64_t k = ((uint64_t)rh << 32) | (rl & 0xfffff800u);
+    return __ull2float_rn(k) * 0x1p-64f;
+}
+
+// v5: v4 with the 64-bit add as IMAD.WIDE (s0.lo * 1 + s1) + IMAD.IADD on the FMA pipe
+__device__ __forceinline__ float draw_v5(H &s, const M m) {
+    const uint64_t sum = (uint64_t)s.a * m.one + (((uint64_t)s.d << 32) | s.c);
+    const uint32_t rl = (uint32_t)sum, rh = (uint32_t)(sum >> 32) + s.b;
+    const uint32_t tl = s.a ^ s.c, th = s.b ^ s.d;
+    const uint32_t ql = __funnelshift_r(s.a, s.b, 9), qh = __funnelshift_r(s.b, s.a, 9);
+    const uint32_t ul = tl << 14, uh = __funnelshift_l(tl, th, 14);
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s.a) : "r"(ql), "r"(tl), "r"(ul));
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s.b) : "r"(qh), "r"(th), "r"(uh));
+    s.c = __funnelshift_l(tl, th, 4);
+    s.d = __funnelshift_l(th, tl, 4);
+    const uint64_t k = ((uint64_t)rh << 32) | (rl & 0xfffff800u);
+    return __ull2float_rn(k) * 0x1p-64f;
+}
+
+// v6: v4 with the output mask done on the FMA pipe: (rl >> 11) << 11 as IMAD.HI by 2^21 and
+// IMAD.SHL
+__device__ __forceinline__ float draw_v6(H &s, const M m) {
+    uint32_t rl, rh;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=r"(rl), "=r"(rh) : "r"(s.a), "r"(s.c), "r"(s.b), "r"(s.d));
+    const uint32_t tl = s.a ^ s.c, th = s.b ^ s.d;
+    const uint32_t ql = __funnelshift_r(s.a, s.b, 9), qh = __funnelshift_r(s.b, s.a, 9);
+    const uint32_t ul = tl << 14, uh = __funnelshift_l(tl, th, 14);
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s.a) : "r"(ql), "r"(tl), "r"(ul));
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s.b) : "r"(qh), "r"(th), "r"(uh));
+    s.c = __funnelshift_l(tl, th, 4);
+    s.d = __funnelshift_l(th, tl, 4);
+    const uint32_t rlm = __umulhi(rl, m.m21) * m.m11;
+    const uint64_t k = ((uint64_t)rh << 32) | rlm;
+    return __ull2float_rn(k) * 0x1p-64f;
+}
+
 template <int V>
 __global__ void __launch_bounds__(256) bench(const S *in, float *out, int draws, M m) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -65,7 +112,9 @@ __global__ void __launch_bounds__(256) bench(const S *in, float *out, int draws,
         for (int k = 0; k < draws; ++k) acc += draw_v1(s0, s1);
     } else {
         H h{(uint32_t)st.s0, (uint32_t)(st.s0 >> 32), (uint32_t)st.s1, (uint32_t)(st.s1 >> 32)};
-        for (int k = 0; k < draws; ++k) acc += (V == 2) ? draw_v2(h) : draw_v3(h, m);
+        for (int k = 0; k < draws; ++k)
+            acc += (V == 2) ? draw_v2(h) : (V == 3) ? draw_v3(h, m) : (V == 4) ? draw_v4(h)
+                   : (V == 5) ? draw_v5(h, m) : draw_v6(h, m);
     }
     out[i] = acc;
 }
@@ -80,21 +129,24 @@ int main() {
         z = z * 6364136223846793005ull + 1442695040888963407ull;
         h[i].s1 = z;
     }
-    S *d_in; float *d_out[3];
+    S *d_in; float *d_out[6];
     cudaMalloc(&d_in, sizeof(S) * threads);
     cudaMemcpy(d_in, h, sizeof(S) * threads, cudaMemcpyHostToDevice);
-    for (int v = 0; v < 3; ++v) cudaMalloc(&d_out[v], sizeof(float) * threads);
-    const M m{1u << 23, 1u << 14, 1u << 4, 1u};
+    for (int v = 0; v < 6; ++v) cudaMalloc(&d_out[v], sizeof(float) * threads);
+    const M m{1u << 23, 1u << 14, 1u << 4, 1u, 1u << 21, 1u << 11};
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    float *host[3];
-    for (int v = 0; v < 3; ++v) {
+    float *host[6];
+    for (int v = 0; v < 6; ++v) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; ++rep) {
             cudaEventRecord(e0);
             if (v == 0) bench<1><<<threads / 256, 256>>>(d_in, d_out[v], draws, m);
             if (v == 1) bench<2><<<threads / 256, 256>>>(d_in, d_out[v], draws, m);
             if (v == 2) bench<3><<<threads / 256, 256>>>(d_in, d_out[v], draws, m);
+            if (v == 3) bench<4><<<threads / 256, 256>>>(d_in, d_out[v], draws, m);
+            if (v == 4) bench<5><<<threads / 256, 256>>>(d_in, d_out[v], draws, m);
+            if (v == 5) bench<6><<<threads / 256, 256>>>(d_in, d_out[v], draws, m);
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -106,8 +158,10 @@ int main() {
         printf("v%d: %.3f ms  %.1f Gdraws/s  %.2f cycles/draw/SMSP-warp @1.9GHz (err=%s)\n", v + 1, best,
                dps / 1e9, 148.0 * 4 * 1.9e9 * 32 / dps, cudaGetErrorString(cudaGetLastError()));
     }
-    int bad2 = 0, bad3 = 0;
-    for (int i = 0; i < threads; ++i) { bad2 += host[0][i] != host[1][i]; bad3 += host[0][i] != host[2][i]; }
-    printf("mismatch v2=%d v3=%d\n", bad2, bad3);
+    for (int v = 1; v < 6; ++v) {
+        int bad = 0;
+        for (int i = 0; i < threads; ++i) bad += host[0][i] != host[v][i];
+        printf("mismatch v%d=%d\n", v + 1, bad);
+    }
     return 0;
 }
