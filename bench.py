@@ -171,6 +171,10 @@ def run_ours(args):
 
     renderer = render.FastRenderer(samples_per_pixel=SPP, device=local_rank)
     ctx = renderer.context
+    if args.contexts is not None:
+        from reinfocus_b200 import _lib as native
+
+        ctx.set_option(native.OPT_TRACE_CONTEXTS, args.contexts)
     info = ctx.device_info()
 
     def barrier():
@@ -290,7 +294,8 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {
-            "kernel": "rf::trace_kernel", "bound": "fp32",
+            "kernel": "rf::trace_mc_kernel" if ctx.last_trace_kernel() > 1 else "rf::trace_kernel",
+            "pixels_per_thread": max(ctx.last_trace_kernel(), 1), "bound": "fp32",
             "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / fp32_peak if fp32_peak else None,
             "traffic": scaled_traffic("trace_kernel_bytes_per_env"),
@@ -332,6 +337,8 @@ def main():
     parser.add_argument("--envs", type=int, default=4096)
     parser.add_argument("--impl", choices=["ours", "reference"], default="ours")
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--contexts", type=int, default=None,
+                        help="pixels per thread of the tracer (0, 2, 4, 8); default: library default")
     args = parser.parse_args()
     assert args.warmup >= 1
     if args.impl == "reference":

@@ -23,6 +23,7 @@ ABI_VERSION = 2
 
 SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH = 0, 1, 2
 OPT_FORCE_GENERIC = 0
+OPT_TRACE_CONTEXTS = 1
 INFO_LAST_TRACE_KERNEL = 0
 INFO_LAST_FOCUS_KERNEL = 1
 

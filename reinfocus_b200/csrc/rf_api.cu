@@ -58,6 +58,7 @@ struct rf_ctx {
     unsigned long long *d_misc = nullptr;  // small scratch (selftests)
 
     bool force_generic = false;  // RF_OPT_FORCE_GENERIC
+    int trace_contexts = 4;      // RF_OPT_TRACE_CONTEXTS: pixels per thread of the default-camera kernel
     int last_kernel = -1;        // 0 generic, 1 fast (introspection for tests)
     int last_focus_kernel = -1;  // 0 staged (general), 1 packed
 };
@@ -177,11 +178,35 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
     const bool fast = !ctx->force_generic && ctx->u[0] == 1.0f && ctx->u[1] == 0.0f &&
                       ctx->u[2] == 0.0f && ctx->v[0] == 0.0f && ctx->v[1] == 1.0f &&
                       ctx->v[2] == 0.0f && ctx->lens_radius == 0.05;
-    if (fast)
+    const int contexts = fast ? ctx->trace_contexts : 0;
+    if (contexts > 0) {
+        // multi-context kernel: blocks are per env, kCtx * kMcThreads pixels each
+        const int per_block = contexts * rf::kMcThreads;
+        const int blocks_per_env = (H * W + per_block - 1) / per_block;
+        const int64_t grid = (int64_t)n * blocks_per_env;
+        if (grid > 0x7fffffffLL) return fail(ctx, RF_ERR_INVALID, "render batch too large");
+        const size_t smem = (size_t)per_block * sizeof(rf::McSlots);
+        switch (contexts) {
+            case 2:
+                rf::trace_mc_kernel<2><<<(unsigned)grid, rf::kMcThreads, smem, stream>>>(p, blocks_per_env);
+                break;
+            case 4:
+                rf::trace_mc_kernel<4><<<(unsigned)grid, rf::kMcThreads, smem, stream>>>(p, blocks_per_env);
+                break;
+            case 8:
+                RF_CUDA(ctx, cudaFuncSetAttribute(rf::trace_mc_kernel<8>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                rf::trace_mc_kernel<8><<<(unsigned)grid, rf::kMcThreads, smem, stream>>>(p, blocks_per_env);
+                break;
+            default:
+                return fail(ctx, RF_ERR_INVALID, "unsupported context count %d", contexts);
+        }
+    } else if (fast) {
         rf::trace_kernel<true><<<(unsigned)blocks, rf::kTraceThreads, 0, stream>>>(p);
-    else
+    } else {
         rf::trace_kernel<false><<<(unsigned)blocks, rf::kTraceThreads, 0, stream>>>(p);
-    ctx->last_kernel = fast ? 1 : 0;
+    }
+    ctx->last_kernel = contexts > 0 ? contexts : (fast ? 1 : 0);
     ctx->launches++;
     RF_CUDA(ctx, cudaGetLastError());
     return RF_OK;
@@ -641,6 +666,11 @@ int rf_set_option(rf_ctx *ctx, int option, int value) {
     switch (option) {
         case RF_OPT_FORCE_GENERIC:
             ctx->force_generic = value != 0;
+            return RF_OK;
+        case RF_OPT_TRACE_CONTEXTS:
+            if (value != 0 && value != 2 && value != 4 && value != 8)
+                return fail(ctx, RF_ERR_INVALID, "RF_OPT_TRACE_CONTEXTS must be 0, 2, 4 or 8");
+            ctx->trace_contexts = value;
             return RF_OK;
         default:
             return fail(ctx, RF_ERR_INVALID, "rf_set_option: unknown option %d", option);
