@@ -278,9 +278,12 @@ __global__ void __launch_bounds__(kPackedWarps * 32) focus_packed_kernel(const P
     uint32_t sum = 0, sum2 = 0;
     const uint32_t bias = 1020u | (1020u << 16), top = 1275u | (1275u << 16);
 
+    // the next row's gray word is requested one iteration ahead so that its latency hides
+    // behind the current row's arithmetic
+    uint32_t g_next = load_gray_word<kChannels>(img + min(max(y0 - 2, 0), H - 1) * pitch, x0, W);
     for (int r = y0 - 2; r <= y1 + 1; ++r) {
-        const int ry = min(max(r, 0), H - 1);
-        const uint32_t g = load_gray_word<kChannels>(img + ry * pitch, x0, W);
+        const uint32_t g = g_next;
+        if (r <= y1) g_next = load_gray_word<kChannels>(img + min(max(r + 1, 0), H - 1) * pitch, x0, W);
         const uint32_t gl = __shfl_up_sync(0xffffffffu, g, 1);
         const uint32_t gr = __shfl_down_sync(0xffffffffu, g, 1);
         // zero-extended column pairs (x0-1,x0) (x0,x0+1) (x0+1,x0+2) (x0+2,x0+3) (x0+3,x0+4)

@@ -616,3 +616,22 @@ def test_generic_render_matches_oracle_on_a_random_scene(torch):
     want = oracle.render_generic(params, types, sizes, cameras.device_data(), (37, 53), 9)
     mismatch = int((got != want).sum())
     assert mismatch <= got.size * 1e-4, f"{mismatch} of {got.size} bytes differ"
+
+
+# ------------------------------------------------------ PPO rollout collection (config 5)
+
+
+def test_ppo_rollout_and_update_run_on_the_vector_env(torch):
+    """examples/ppo.py: one 32-step rollout on 6 envs with frame stack + normalisation, then a
+    few PPO minibatches; the buffer has the ppo_tuned.yml shapes and the losses are finite."""
+
+    from examples import ppo
+
+    cfg = ppo.PPOConfig.from_yml(os.path.join(REPO, "examples", "ppo_tuned.yml"), "DiscreteSteps-v0")
+    assert (cfg.n_steps, cfg.frame_stack, cfg.net_arch if isinstance(cfg.net_arch, tuple) else None) == (
+        32, 5, (256, 256))
+    history = ppo.train(num_envs=6, rollouts=1, config=cfg, max_minibatches=3, log=lambda e: None)
+    entry = history[0]
+    assert entry["env_steps"] == 6 * 32
+    assert all(numpy.isfinite(entry[k]) for k in ("loss", "pg", "vf", "entropy", "mean_reward"))
+    assert 0 < entry["entropy"] <= numpy.log(13) + 1e-6
