@@ -118,13 +118,14 @@ def _f3(values):
     return (ctypes.c_float * 3)(*[float(v) for v in values])
 
 
-def _stream_ptr(stream=None):
-    """The cudaStream_t to launch on: torch's current stream unless one is given."""
+def _stream_ptr(stream=None, device=None):
+    """The cudaStream_t to launch on: torch's current stream on the context's device unless
+    one is given."""
 
     if stream is None:
         import torch
 
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     if hasattr(stream, "cuda_stream"):
         return ctypes.c_void_p(stream.cuda_stream)
     return ctypes.c_void_p(int(stream))
@@ -186,7 +187,7 @@ class Context:
     def rng_ensure(self, n_states: int, seed: int = 0, stream=None):
         self._check(self._lib.rf_rng_ensure(self._handle, int(n_states),
                                             ctypes.c_uint64(seed & (2**64 - 1)),
-                                            _stream_ptr(stream)))
+                                            _stream_ptr(stream, self.device)))
 
     def rng_reset(self):
         self._check(self._lib.rf_rng_reset(self._handle))
@@ -207,26 +208,26 @@ class Context:
     def rng_init_device(self, d_states_ptr: int, n: int, seed: int, stream=None):
         self._check(self._lib.rf_rng_init_device(self._handle, _vp(d_states_ptr), int(n),
                                                  ctypes.c_uint64(seed & (2**64 - 1)),
-                                                 _stream_ptr(stream)))
+                                                 _stream_ptr(stream, self.device)))
 
     def rng_uniform_device(self, d_states_ptr: int, n: int, draws: int, d_out_ptr: int,
                            stream=None):
         self._check(self._lib.rf_rng_uniform_device(self._handle, _vp(d_states_ptr), int(n),
                                                     int(draws), _vp(d_out_ptr),
-                                                    _stream_ptr(stream)))
+                                                    _stream_ptr(stream, self.device)))
 
     # ------------------------------------------------------------------------- scene
     def set_world(self, world: numpy.ndarray, stream=None):
         world = numpy.ascontiguousarray(world, dtype=numpy.float32).reshape(-1, 2)
         self._check(self._lib.rf_set_world(self._handle, len(world), world.ctypes.data,
-                                           _stream_ptr(stream)))
+                                           _stream_ptr(stream, self.device)))
         # the copy is stream-ordered from pageable memory: CUDA stages it before returning
 
     def set_cameras(self, cam_dyn: numpy.ndarray, origin, u, v, lens_radius: float, stream=None):
         cam_dyn = numpy.ascontiguousarray(cam_dyn, dtype=numpy.float32).reshape(-1, 9)
         self._check(self._lib.rf_set_cameras(self._handle, len(cam_dyn), cam_dyn.ctypes.data,
                                              _f3(origin), _f3(u), _f3(v), float(lens_radius),
-                                             _stream_ptr(stream)))
+                                             _stream_ptr(stream, self.device)))
 
     def scene_envs(self) -> int:
         return int(self._lib.rf_scene_envs(self._handle))
@@ -235,7 +236,7 @@ class Context:
     def render(self, n: int, height: int, width: int, spp: int, d_rgb: int | None,
                d_gray: int | None, stream=None):
         self._check(self._lib.rf_render(self._handle, n, height, width, spp, _vp(d_rgb),
-                                        _vp(d_gray), _stream_ptr(stream)))
+                                        _vp(d_gray), _stream_ptr(stream, self.device)))
 
     def render_generic(self, shape_params: numpy.ndarray, shape_types: numpy.ndarray,
                        env_sizes: numpy.ndarray, cameras: numpy.ndarray, height: int, width: int,
@@ -250,28 +251,28 @@ class Context:
         self._check(self._lib.rf_render_generic(
             self._handle, n, height, width, spp, max_shapes, shape_params.ctypes.data,
             shape_types.ctypes.data, env_sizes.ctypes.data, cameras.ctypes.data,
-            ctypes.c_uint64(seed & (2**64 - 1)), _vp(d_rgb), _stream_ptr(stream)))
+            ctypes.c_uint64(seed & (2**64 - 1)), _vp(d_rgb), _stream_ptr(stream, self.device)))
 
     def focus(self, n: int, height: int, width: int, d_img: int, channels: int, d_out: int,
               d_median: int | None = None, d_laplacian: int | None = None, stream=None):
         self._check(self._lib.rf_focus_planes(self._handle, n, height, width, _vp(d_img),
                                               channels, _vp(d_out), _vp(d_median),
-                                              _vp(d_laplacian), _stream_ptr(stream)))
+                                              _vp(d_laplacian), _stream_ptr(stream, self.device)))
 
     def step_host(self, n: int, height: int, spp: int, h_world: int | None,
                   h_cam_dyn: int | None, h_focus: int, stream=None):
         self._check(self._lib.rf_step_host(self._handle, n, height, spp, _vp(h_world),
-                                           _vp(h_cam_dyn), _vp(h_focus), _stream_ptr(stream)))
+                                           _vp(h_cam_dyn), _vp(h_focus), _stream_ptr(stream, self.device)))
 
     def step_device(self, n: int, height: int, spp: int, d_focus: int, stream=None):
         self._check(self._lib.rf_step_device(self._handle, n, height, spp, _vp(d_focus),
-                                             _stream_ptr(stream)))
+                                             _stream_ptr(stream, self.device)))
 
     # ------------------------------------------------------------------- self-checks
     def selftest(self, which: int, arg: int = 0, stream=None) -> int:
         bad = ctypes.c_int64(-1)
         self._check(self._lib.rf_selftest(self._handle, which, arg, ctypes.byref(bad),
-                                          _stream_ptr(stream)))
+                                          _stream_ptr(stream, self.device)))
         return bad.value
 
     def selftest_checker(self, stream=None) -> int:
