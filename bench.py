@@ -151,6 +151,9 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, which must carry one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import numpy
     import torch
     import torch.distributed as dist
