@@ -293,7 +293,8 @@ def run_ours(args):
         },
         "rays_per_s": args.envs * HEIGHT * HEIGHT * SPP / (device_ms * 1e-3),
         "e2e": {"value": args.envs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": n_local * (2 + 9) * 4, "d2h_bytes_per_step": n_local * 8},
+                "h2d_bytes_per_step": args.envs * (2 + 9) * 4, "d2h_bytes_per_step": args.envs * 8,
+                "bytes_note": "whole job; each rank copies 1/n_gpus of it"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {

@@ -227,6 +227,34 @@ def test_full_size_frame_matches_oracle(torch):
     numpy.testing.assert_array_equal(gpu.context.rng_export(), cpu.states)
 
 
+@pytest.mark.parametrize("height,spp,n", [(1, 9, 2), (2, 5, 3), (3, 4, 1), (5, 3, 4), (1200, 2, 1), (601, 1, 2)])
+def test_extreme_frame_sizes_match_oracle(torch, height, spp, n):
+    """Tiny frames (1 .. 5 pixels a side: every block is ragged) and the largest sweep size."""
+
+    targets = [5.0, 10.0, 7.25, 8.5][:n]
+    planes = [10.0, 5.0, 7.25, 6.0][:n]
+    gpu = _renderer(samples_per_pixel=spp)
+    cpu = oracle.OracleFastRenderer(samples_per_pixel=spp, profile=oracle.PROFILE_GPU)
+    for renderer in (gpu, cpu):
+        renderer.update_targets(targets)
+        renderer.update_focus_planes(planes)
+    got, want = gpu.render(height), cpu.render(height)
+    assert int((got != want).sum()) == 0
+    numpy.testing.assert_array_equal(gpu.step_focus(targets, planes, height),
+                                     oracle.focus_values(cpu.render(height)))
+
+
+def test_empty_batches(torch):
+    from reinfocus_b200 import vision
+
+    assert vision.focus_values(numpy.zeros((0, 8, 8, 3), dtype=numpy.uint8)) == []
+    renderer = _renderer()
+    renderer.update_targets([])
+    renderer.update_focus_planes([])
+    with pytest.raises(AssertionError):
+        renderer.render(8)
+
+
 def test_rng_state_cache_semantics(torch):
     """reference render.py:248-257: states persist, and are re-created from seed 0 only when
     a call needs more than exist; a smaller later call reuses the larger cache."""
