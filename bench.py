@@ -250,6 +250,28 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
 
+    # ------------- the real vector env (DiscreteSteps-v0): transform, observe (render + focus),
+    # reward, end, and the same-step re-render of the envs that were reset
+    from examples import custom_environments
+    from reinfocus_b200.environments import state_initializer
+
+    env = custom_environments.VectorDiscreteSteps(
+        max_episode_steps=20, num_envs=n_local,
+        initializer=state_initializer.RangedInitializer([[custom_environments.ENDS]] * 2, seed=1234 + rank))
+    action_rng = numpy.random.Generator(numpy.random.PCG64DXSM(4321 + rank))
+    env.reset()
+    resets = 0
+    for _ in range(args.warmup):
+        env.step(action_rng.integers(0, 13, n_local))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, terminated, truncated, _ = env.step(action_rng.integers(0, 13, n_local))
+        resets += int((terminated | truncated).sum())
+    barrier()
+    env_loop_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    del env
+
     if rank != 0:
         return
 
@@ -317,6 +339,12 @@ def run_ours(args):
             "traffic": scaled_traffic("focus_kernel_bytes_per_env"),
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
             "launch_ms": focus_ms, "algorithmic_bytes_per_launch": focus_bytes,
+        },
+        "env_loop": {
+            "what": "VectorDiscreteSteps.step with uniform random actions: transform + render + "
+                    "focus + rewards + enders + same-step re-render of reset envs, host API",
+            "value": args.envs / (env_loop_ms * 1e-3), "unit": UNIT, "ms_per_step": env_loop_ms,
+            "resets_per_step_rank0": resets / args.steps,
         },
         "rng_init_s": rng_init_s,
         "device": {"sm_count": info["sm_count"], "cc": list(info["cc"])},

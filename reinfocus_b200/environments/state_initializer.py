@@ -31,6 +31,14 @@ class RangedInitializer:
         self._ranges = ranges
 
     def initialize(self, num_envs: int) -> NDArray[numpy.float32]:
+        if all(len(options) == 1 for options in self._ranges):
+            # one range per element (every example env): choosing among one option consumes
+            # no randomness, so the per-env loop below draws exactly one double per element
+            # in env-major order - which is what a single vectorised uniform() draws
+            low = numpy.array([options[0][0] for options in self._ranges], dtype=numpy.float64)
+            high = numpy.array([options[0][1] for options in self._ranges], dtype=numpy.float64)
+            return self._generator.uniform(low, high, size=(num_envs, len(self._ranges))).astype(
+                numpy.float32)
         states = numpy.empty((num_envs, len(self._ranges)), dtype=numpy.float32)
         for env in range(num_envs):
             for element, options in enumerate(self._ranges):

@@ -77,3 +77,16 @@ def test_registry_builds_example_envs_lazily():
     assert spec.max_episode_steps == 20
     assert gym_compat._load_entry_point(spec.vector_entry_point).__name__ == "VectorDiscreteSteps"
     assert gym_compat._load_entry_point(spec.entry_point).__name__ == "DiscreteSteps"
+
+
+def test_vectorised_initializer_draws_the_same_states_as_the_reference_loop(modules):
+    """RangedInitializer's fast path (one range per element) against the reference's draw
+    order: per env, per element, choice() then uniform() on one PCG64DXSM stream."""
+
+    ranges = [[(5.0, 10.0)], [(5.0, 10.0)], [(-1.0, 2.5)]]
+    fast = modules.state_initializer.RangedInitializer(ranges, seed=99)
+    reference_order = numpy.random.Generator(numpy.random.PCG64DXSM(99))
+    for count in (1, 7, 300):
+        want = numpy.array([[reference_order.uniform(*reference_order.choice(r)) for r in ranges]
+                            for _ in range(count)], dtype=numpy.float32)
+        numpy.testing.assert_array_equal(fast.initialize(count), want)
