@@ -6,12 +6,31 @@ from __future__ import annotations
 
 import abc
 from collections.abc import Callable
-from typing import Any
+from typing import Any, Protocol
 
 import numpy
 from numpy.typing import NDArray
 
 from reinfocus_b200 import histories
+
+
+class IEpisodeEnder(Protocol):
+    """The interface episode enders follow (reference episode_ender.py:18-83)."""
+
+    def step(self, states: Any):
+        ...
+
+    def is_terminated(self) -> NDArray[numpy.bool_]:
+        ...
+
+    def is_truncated(self) -> NDArray[numpy.bool_]:
+        ...
+
+    def reset(self, states: Any, indices: NDArray[numpy.bool_] | None = None):
+        ...
+
+    def status(self, index: int) -> str:
+        ...
 
 
 def _all_envs(num_envs: int, indices):

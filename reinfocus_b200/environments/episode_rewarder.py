@@ -5,9 +5,20 @@ expression, because the reward sequence is part of the parity contract."""
 from __future__ import annotations
 
 from collections.abc import Callable
+from typing import Protocol
 
 import numpy
 from numpy.typing import NDArray
+
+
+class IEpisodeRewarder(Protocol):
+    """The interface rewarders follow (reference episode_rewarder.py:15-60)."""
+
+    def reset(self, states, observations, indices: NDArray[numpy.bool_] | None = None):
+        ...
+
+    def reward(self, states, observations) -> NDArray[numpy.float32]:
+        ...
 
 
 class BaseRewarder:

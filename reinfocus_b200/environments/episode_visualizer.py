@@ -5,6 +5,8 @@ through the SHARED renderer, which advances / re-creates its RNG states and so p
 every later observation. matplotlib and cv2 are imported
 lazily: constructing an env must work on machines without them."""
 
+from typing import Protocol
+
 import numpy
 from numpy.typing import NDArray
 
@@ -19,6 +21,19 @@ def fading_colours(cmap, max_n: int, n: int, p: int = 2):
     colours = cmap(samples)
     colours[:, -1] = samples
     return colours
+
+
+class IEpisodeVisualizer(Protocol):
+    """The interface visualizers follow (reference episode_visualizer.py:43-84)."""
+
+    def step(self, states, observations, indices=None):
+        ...
+
+    def reset(self, states, observations, indices=None):
+        ...
+
+    def visualize(self) -> NDArray[numpy.uint8]:
+        ...
 
 
 class HistoryVisualizer:

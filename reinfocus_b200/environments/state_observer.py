@@ -5,7 +5,7 @@ frame off the GPU (FastRenderer.step_focus)."""
 
 import functools
 from collections.abc import Sequence
-from typing import SupportsFloat
+from typing import Protocol, SupportsFloat
 
 import numpy
 from numpy.typing import NDArray
@@ -14,6 +14,19 @@ from reinfocus_b200 import gym_compat
 from reinfocus_b200.graphics import render
 
 spaces = gym_compat.spaces
+
+
+class IStateObserver(Protocol):
+    """The interface observers follow (reference state_observer.py:21-54)."""
+
+    observation_space: object
+    single_observation_space: object
+
+    def observe(self, states, indices: NDArray[numpy.bool_] | None = None):
+        ...
+
+    def reset(self, states, indices: NDArray[numpy.bool_] | None = None):
+        ...
 
 
 class BaseObserver:

@@ -2,6 +2,7 @@
 
 import abc
 from collections.abc import Collection
+from typing import Protocol
 
 import numpy
 from numpy.typing import NDArray
@@ -9,6 +10,17 @@ from numpy.typing import NDArray
 from reinfocus_b200 import gym_compat
 
 spaces = gym_compat.spaces
+
+
+class IStateTransformer(Protocol):
+    # pylint: disable=too-few-public-methods
+    """The interface transformers follow (reference state_transformer.py:18-38)."""
+
+    action_space: object
+    single_action_space: object
+
+    def transform(self, states, actions):
+        ...
 
 
 class StateTransformer(abc.ABC):

@@ -40,7 +40,8 @@ class DeviceData(abc.ABC):
                 and numpy.array_equal(self._data, data)):
             return
         self._data = data.copy()
-        self._packed = self._make_device_data(self._data)
+        # the transform sees the caller's array, as in the reference (device_data.py:64-66)
+        self._packed = self._make_device_data(data)
         self._version += 1
 
     @abc.abstractmethod
