@@ -9,7 +9,8 @@ loaded from its tests directory:
 --tests-root defaults to /root/reference (build container) or baseline/_ref (GPU box, where
 oracle/gen_golden_gpu.py's copy of the reference lives; add its tests/ directory there).
 Without --gpu only the host-side suites run (env layer, histories, device_data,
-shape_factory); with --gpu also vision, FocusObserver and the episode visualizer. The
+shape_factory); with --gpu also vision and FocusObserver (and the episode visualizer tests
+when matplotlib is installed). The
 reference's numba device-function tests (camera/physics/rectangle/... via ad-hoc @cuda.jit
 kernels) have no counterpart here: those functions are inlined in the CUDA kernels and are
 covered by the bit-exact frame comparisons instead."""
@@ -35,7 +36,9 @@ HOST_SUITES = [
 ]
 # state_observer_test mixes host-only cases with FocusObserverTest (needs the GPU)
 OBSERVER_SUITE = "tests.environments.state_observer_test"
-GPU_SUITES = ["tests.vision_test", "tests.environments.episode_visualizer_test"]
+GPU_SUITES = ["tests.vision_test"]
+# needs the real matplotlib (colormaps); not installable offline
+PLOT_SUITES = ["tests.environments.episode_visualizer_test"]
 
 
 def install_aliases():
@@ -66,7 +69,13 @@ def run(tests_root: str, gpu: bool, verbosity: int = 1):
     sys.path.insert(0, tests_root)
     suite = unittest.TestSuite()
     loader = unittest.defaultTestLoader
-    for name in HOST_SUITES + (GPU_SUITES if gpu else []):
+    try:
+        import matplotlib.colors
+
+        have_plot = hasattr(matplotlib.colors, "LinearSegmentedColormap")
+    except ImportError:
+        have_plot = False
+    for name in HOST_SUITES + (GPU_SUITES if gpu else []) + (PLOT_SUITES if gpu and have_plot else []):
         suite.addTests(loader.loadTestsFromName(name))
     observer = loader.loadTestsFromName(OBSERVER_SUITE)
 
