@@ -175,8 +175,15 @@ int rf_step_device(rf_ctx *ctx, int n, int H, int spp, double *d_focus, void *st
  *                           float32((x + U) / arg), every x in [0, arg), every float32 U in
  *                           [0, 1] (arg = frame width or height);
  *   RF_SELFTEST_INV_LENGTH  branch-free 1/sqrt-length vs __frcp_rn(__fsqrt_rn()) for every
- *                           float32 in [2^-60, 2^60]. */
-enum { RF_SELFTEST_CHECKER = 0, RF_SELFTEST_PIXEL_DIV = 1, RF_SELFTEST_INV_LENGTH = 2 };
+ *                           float32 in [2^-60, 2^60];
+ *   RF_SELFTEST_CONST_DIV   hoisted-reciprocal float32 division vs __fdiv_rn for every
+ *                           numerator in [0, c], over `arg` divisors c spread over [0.5, 8). */
+enum {
+    RF_SELFTEST_CHECKER = 0,
+    RF_SELFTEST_PIXEL_DIV = 1,
+    RF_SELFTEST_INV_LENGTH = 2,
+    RF_SELFTEST_CONST_DIV = 3
+};
 int rf_selftest(rf_ctx *ctx, int which, int arg, int64_t *mismatches, void *stream);
 /* Options. RF_OPT_FORCE_GENERIC = 1 makes rf_render use the literal any-camera kernel and
  * rf_focus the general staged kernel even when the specialised ones apply (A/B parity

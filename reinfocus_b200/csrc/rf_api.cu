@@ -706,6 +706,10 @@ int rf_selftest(rf_ctx *ctx, int which, int arg, int64_t *mismatches, void *stre
         case RF_SELFTEST_INV_LENGTH:
             rf::inv_length_selftest_kernel<<<blocks, 256, 0, s>>>(ctx->d_misc);
             break;
+        case RF_SELFTEST_CONST_DIV:
+            RF_REQUIRE(ctx, arg > 0 && arg <= 4096, "rf_selftest: divisor count out of range");
+            rf::const_div_selftest_kernel<<<blocks, 256, 0, s>>>(arg, ctx->d_misc);
+            break;
         default:
             return fail(ctx, RF_ERR_INVALID, "rf_selftest: unknown test %d", which);
     }

@@ -113,6 +113,15 @@ def test_branch_free_inverse_length_equals_intrinsics_for_every_input(ctx):
     assert ctx.selftest(_lib.SELFTEST_INV_LENGTH) == 0
 
 
+def test_hoisted_reciprocal_float32_division_equals_fdiv(ctx):
+    """(r + P) / (r + r) with the reciprocal refinement hoisted: every numerator in [0, c] for
+    96 divisors c spread over [0.5, 8)."""
+
+    from reinfocus_b200 import _lib
+
+    assert ctx.selftest(_lib.SELFTEST_CONST_DIV, 96) == 0
+
+
 @pytest.mark.parametrize("targets,planes,height,spp", [
     ([7.5, 5.0, 10.0, 6.3], [7.5, 10.0, 5.0, 6.3], 40, 12),
     ([9.0, 5.5], [5.25, 9.75], 97, 5),
