@@ -58,7 +58,7 @@ struct rf_ctx {
     unsigned long long *d_misc = nullptr;  // small scratch (selftests)
 
     bool force_generic = false;  // RF_OPT_FORCE_GENERIC
-    int trace_contexts = 4;      // RF_OPT_TRACE_CONTEXTS: pixels per thread of the default-camera kernel
+    int trace_contexts = -1;     // RF_OPT_TRACE_CONTEXTS: pixels per thread of the default-camera kernel (-1 = by batch size)
     int last_kernel = -1;        // 0 generic, 1 fast (introspection for tests)
     int last_focus_kernel = -1;  // 0 staged (general), 1 packed
 };
@@ -178,7 +178,13 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
     const bool fast = !ctx->force_generic && ctx->u[0] == 1.0f && ctx->u[1] == 0.0f &&
                       ctx->u[2] == 0.0f && ctx->v[0] == 0.0f && ctx->v[1] == 1.0f &&
                       ctx->v[2] == 0.0f && ctx->lens_radius == 0.05;
-    const int contexts = fast ? ctx->trace_contexts : 0;
+    // four pixels per thread trade parallelism for fewer divergent rejection-loop trips:
+    // that pays once the batch fills every SM several times over (measured: from ~20 envs
+    // of 300x300 on; below that one pixel per thread has the lower step latency)
+    int contexts = ctx->trace_contexts;
+    if (contexts < 0)
+        contexts = p.total >= (int64_t)ctx->prop.multiProcessorCount * 2048 * 6 ? 4 : 0;
+    if (!fast) contexts = 0;
     if (contexts > 0) {
         // multi-context kernel: blocks are per env, kCtx * kMcThreads pixels each
         const int per_block = contexts * rf::kMcThreads;
@@ -668,8 +674,8 @@ int rf_set_option(rf_ctx *ctx, int option, int value) {
             ctx->force_generic = value != 0;
             return RF_OK;
         case RF_OPT_TRACE_CONTEXTS:
-            if (value != 0 && value != 2 && value != 4 && value != 8)
-                return fail(ctx, RF_ERR_INVALID, "RF_OPT_TRACE_CONTEXTS must be 0, 2, 4 or 8");
+            if (value != -1 && value != 0 && value != 2 && value != 4 && value != 8)
+                return fail(ctx, RF_ERR_INVALID, "RF_OPT_TRACE_CONTEXTS must be -1, 0, 2, 4 or 8");
             ctx->trace_contexts = value;
             return RF_OK;
         default:

@@ -90,3 +90,51 @@ def test_vectorised_initializer_draws_the_same_states_as_the_reference_loop(modu
         want = numpy.array([[reference_order.uniform(*reference_order.choice(r)) for r in ranges]
                             for _ in range(count)], dtype=numpy.float32)
         numpy.testing.assert_array_equal(fast.initialize(count), want)
+
+
+def test_sb3_adapter_follows_the_vec_env_protocol(modules):
+    """SB3Wrapper (reference vector_shim.py:20-186) over the discrete vector composition:
+    step_async/step_wait return what VectorEnvironment.step returns with done = terminated
+    | truncated, per-env info dicts and the terminal observation row on finished envs."""
+
+    from reinfocus_b200.environments.experimental import vector_shim
+
+    focus_cls = gen_golden_env.make_analytic_observer(modules.state_observer)
+    cases = gen_golden_env.sim_cases()
+    env, actions, _ = cases["discrete_vector"](modules, focus_cls)
+    twin, _, _ = cases["discrete_vector"](modules, focus_cls)
+    gen_golden_env._seed_initializer(env, 5)
+    gen_golden_env._seed_initializer(twin, 5)
+    wrapped = vector_shim.SB3Wrapper(env, None)
+    assert wrapped.num_envs == 16 and wrapped.render_mode is None
+    assert wrapped.observation_space.shape == (4,) and wrapped.action_space.n == 13
+    numpy.testing.assert_array_equal(wrapped.reset(), twin.reset()[0])
+    saw_done = False
+    for step_actions in actions[:40]:
+        obs, rewards, dones, infos = wrapped.step(step_actions)
+        want_obs, want_rew, term, trunc, _ = twin.step(step_actions)
+        numpy.testing.assert_array_equal(obs, want_obs)
+        numpy.testing.assert_array_equal(rewards, want_rew)
+        numpy.testing.assert_array_equal(dones, term | trunc)
+        assert len(infos) == 16
+        for i, info in enumerate(infos):
+            assert ("terminal_observation" in info) == bool(dones[i])
+            if dones[i]:
+                numpy.testing.assert_array_equal(info["terminal_observation"], obs[i])
+        saw_done |= bool(dones.any())
+    assert saw_done
+    assert wrapped.get_attr("num_envs") == [16] * 16
+    assert wrapped.get_attr("num_envs", 3) == [16] and wrapped.get_attr("num_envs", [1, 2]) == [16, 16]
+    assert wrapped.env_is_wrapped(object) == [False] * 16
+    with pytest.raises(NotImplementedError):
+        wrapped.get_attr("no_such_attribute")
+    with pytest.raises(NotImplementedError):
+        wrapped.set_attr("x", 1)
+    with pytest.raises(NotImplementedError):
+        wrapped.env_method("anything")
+    with pytest.raises(NotImplementedError):
+        vector_shim.SB3Wrapper(object(), None)
+    # without stable-baselines3 there is no DummyVecEnv to swap: the hook is the identity
+    if not vector_shim.HAVE_SB3:
+        marker = object()
+        assert vector_shim.rewrapper(marker) is marker

@@ -169,6 +169,20 @@ def test_multi_context_kernel_equals_literal_kernel(torch, contexts, height, n):
     numpy.testing.assert_array_equal(tested.context.rng_export(), literal.context.rng_export())
 
 
+def test_pixels_per_thread_follow_the_batch_size(torch):
+    """Default option: one pixel per thread for latency-bound small batches, four once
+    the batch fills the GPU several times over; both leave the same frames as the oracle
+    (covered above), here only the choice is checked."""
+
+    small, large = _renderer(samples_per_pixel=1), _renderer(samples_per_pixel=1)
+    small.update_targets([7.0]), small.update_focus_planes([6.0])
+    small.render_gray_device(300)
+    assert small.context.last_trace_kernel() == 1
+    large.update_targets([7.0] * 24), large.update_focus_planes([6.0] * 24)
+    large.render_gray_device(300)
+    assert large.context.last_trace_kernel() == 4
+
+
 def test_literal_kernel_handles_a_non_default_camera(torch):
     """Any origin / basis / lens radius goes through the literal kernel and still matches
     the oracle bit for bit."""
