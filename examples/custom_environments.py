@@ -11,6 +11,7 @@ Common to all three:
 
 import numpy
 
+from reinfocus_b200.environments import device_vector_environment
 from reinfocus_b200.environments import environment
 from reinfocus_b200.environments import episode_ender
 from reinfocus_b200.environments import episode_rewarder
@@ -106,6 +107,26 @@ class VectorDiscreteSteps(vector_environment.VectorEnvironment):
             visualizer=_visualizer(num_envs, renderer, ender),
             num_envs=num_envs,
             render_mode=render_mode,
+        )
+
+
+class DeviceVectorDiscreteSteps(device_vector_environment.DeviceVectorEnvironment):
+    # pylint: disable=too-few-public-methods
+    """VectorDiscreteSteps with the whole step on the GPU: same strategies, same sequences,
+    but states / observations / rewards are torch CUDA tensors and never visit the host
+    (no visualizer, hence no render mode)."""
+
+    def __init__(self, max_episode_steps: int = 20, num_envs: int = 1, initializer=None):
+        renderer = render.FastRenderer()
+        super().__init__(
+            ender=episode_ender.TimeLimitEnder(num_envs, max_episode_steps) | episode_ender.DivergingEnder(
+                num_envs, (TARGET, FOCUS_PLANE), TARGET_RADIUS / 2, early_end_steps=3),
+            initializer=_initializer(initializer),
+            observer=_observer(num_envs, renderer),
+            rewarder=_step_rewarder(),
+            transformer=state_transformer.DiscreteMoveTransformer(num_envs, FOCUS_PLANE, ENDS,
+                                                                  _step_moves()),
+            num_envs=num_envs,
         )
 
 

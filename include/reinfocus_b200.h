@@ -58,6 +58,9 @@ const char *rf_last_error(const rf_ctx *ctx);
 const char *rf_last_global_error(void);
 /* ABI version of this library (bumped on any signature change). */
 int rf_abi_version(void);
+/* sizeof() of the structs passed across this boundary, so a binding can check its layout. */
+enum { RF_SIZEOF_SCENE_PACKING = 0, RF_SIZEOF_ENV_CONFIG = 1 };
+int rf_sizeof(int which);
 /* Device facts the host side sizes launches and rooflines with. */
 int rf_device_info(const rf_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
                    int *clock_khz);
@@ -162,6 +165,86 @@ int rf_focus_planes(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, int 
 int rf_step_host(rf_ctx *ctx, int n, int H, int spp, const float *h_world,
                  const float *h_cam_dyn, double *h_focus, void *stream);
 int rf_step_device(rf_ctx *ctx, int n, int H, int spp, double *d_focus, void *stream);
+
+/* -------------------------------------------------------------------------------------
+ * Scene parameters from device-resident positions. Replaces the host packing of reference
+ * graphics/world.py:107-123 (FastWorlds._make_device_data) and graphics/camera.py:132-179
+ * (FastCameras._make_device_data) plus their uploads: env i takes its target position from
+ * d_targets[i * stride] and its focus-plane distance from d_planes[i * stride] (so an
+ * [n, 2] state tensor is passed as base, base + 1, stride 2). The float32 operations are
+ * the reference's, in its order; the constants are the float32 values the host classes
+ * hold: world_tan = tan(radians(r_size / 2)), half_* = tan(vfov / 2) (* aspect),
+ * full_* = float32(2 * half), and the camera frame origin / u / v / w.
+ * ----------------------------------------------------------------------------------- */
+typedef struct {
+    float world_tan;
+    float half_width, half_height, full_width, full_height;
+    float origin[3], u[3], v[3], w[3];
+    double lens_radius;
+} rf_scene_packing;
+int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float *d_planes,
+                        int stride, const rf_scene_packing *packing, void *stream);
+
+/* -------------------------------------------------------------------------------------
+ * Device-resident vector env. Replaces reference environments/vector_environment.py:75-164
+ * (VectorEnvironment.reset / step) for the strategy compositions of the example envs
+ * (reference examples/custom_environments.py): state [target, focus plane];
+ *   transformer  RF_ENV_DISCRETE_MOVE     DiscreteMoveTransformer (state_transformer.py:222-266)
+ *                RF_ENV_CONTINUOUS_JUMP   ContinuousJumpTransformer (:88-137)
+ *   ender        [TimeLimitEnder |] DivergingEnder (episode_ender.py:590-656, 112-207)
+ *   observer     NormalizedObserver(DeltaObserver([IndexedElementObserver(plane),
+ *                FocusObserver], include_original=True)) (state_observer.py:167-517)
+ *   rewarder     RF_ENV_REWARD_STEPS  DeltaRewarder + ObservationRewarder(1) + OnTargetRewarder
+ *                RF_ENV_REWARD_JUMPS  ObservationRewarder(1) + StoppedRewarder * OnTargetRewarder
+ *                (episode_rewarder.py:86-429)
+ *   initializer  RangedInitializer, one range per element, numpy PCG64DXSM generator
+ *                (state_initializer.py:30-71)
+ * States, observations, rewards and the generator live on the GPU; a step is two small
+ * kernels around the render + focus launches of the context (and of the k restarted envs,
+ * rendered as batch positions 0..k-1 like the reference's partial reset). Sequences are
+ * bit-identical to the host classes driven by the same generator.
+ * ----------------------------------------------------------------------------------- */
+typedef struct rf_env rf_env;
+enum { RF_ENV_DISCRETE_MOVE = 0, RF_ENV_CONTINUOUS_JUMP = 1 };
+enum { RF_ENV_REWARD_STEPS = 0, RF_ENV_REWARD_JUMPS = 1 };
+enum { RF_ENV_ACTIONS_INT32 = 0, RF_ENV_ACTIONS_INT64 = 1, RF_ENV_ACTIONS_FLOAT32 = 2 };
+typedef struct {
+    int num_envs, frame_height, samples_per_pixel;
+    int transformer;
+    int n_moves;             /* <= 32 */
+    double moves[32];        /* discrete action set, float64 as the reference keeps it */
+    float limits[2];         /* clip range of the discrete move / ends of the jump */
+    float jump_span;         /* float32(limits[1] - limits[0]) */
+    float jump_threshold;    /* jumps shorter than this are ignored */
+    int max_steps;           /* time limit, <= 0 for none */
+    float diverge_threshold;
+    int diverge_steps;
+    int rewarder;
+    float delta_reward, delta_scale;
+    float stop_threshold;
+    double stop_reward;
+    float on_span;
+    double on_off, on_delta;
+    float obs_mid[4], obs_scale[4]; /* NormalizedObserver._mid / ._scale */
+    double init_low[2], init_high[2];
+    rf_scene_packing packing;
+} rf_env_config;
+int rf_env_create(rf_ctx *ctx, const rf_env_config *config, rf_env **out);
+int rf_env_destroy(rf_env *env);
+/* numpy.random.PCG64DXSM().state: 128-bit state and increment as (high, low) words. */
+int rf_env_set_generator(rf_env *env, const uint64_t state[2], const uint64_t inc[2]);
+int rf_env_get_generator(rf_env *env, uint64_t state[2], uint64_t inc[2]); /* synchronous */
+/* reset(): every env starts an episode; d_obs float32 [n, 4]. */
+int rf_env_reset(rf_env *env, float *d_obs, void *stream);
+/* step(): d_actions [n] of the given kind; d_obs float32 [n, 4], d_rewards float64 [n],
+ * d_truncated uint8 [n] (nothing ever terminates, as in the reference); *h_resets, if not
+ * NULL, receives the number of envs that restarted. The host waits only for that count,
+ * which is known before the main render starts; the outputs are stream-ordered. */
+int rf_env_step(rf_env *env, const void *d_actions, int action_kind, float *d_obs,
+                double *d_rewards, uint8_t *d_truncated, int *h_resets, void *stream);
+/* Synchronous copies of the env's state (parity tests, checkpoints): any pointer may be
+ * NULL. h_states float32 [n, 2], h_steps / h_diverging int32 [n]. */
+int rf_env_export(rf_env *env, float *h_states, int *h_steps, int *h_diverging);
 
 /* -------------------------------------------------------------------------------------
  * Self-checks and measurement helpers (used by tests/ and bench.py).

@@ -19,7 +19,7 @@ RF_ERR_CUDA = -2
 RF_ERR_NOMEM = -3
 RF_ERR_NO_SCENE = -4
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH, SELFTEST_CONST_DIV = 0, 1, 2, 3
 OPT_FORCE_GENERIC = 0
@@ -27,7 +27,51 @@ OPT_TRACE_CONTEXTS = 1
 INFO_LAST_TRACE_KERNEL = 0
 INFO_LAST_FOCUS_KERNEL = 1
 
+ENV_DISCRETE_MOVE, ENV_CONTINUOUS_JUMP = 0, 1
+ENV_REWARD_STEPS, ENV_REWARD_JUMPS = 0, 1
+ENV_ACTIONS_INT32, ENV_ACTIONS_INT64, ENV_ACTIONS_FLOAT32 = 0, 1, 2
+
 STATE_DTYPE = numpy.dtype([("s0", numpy.uint64), ("s1", numpy.uint64)], align=True)
+
+
+class ScenePacking(ctypes.Structure):
+    """rf_scene_packing."""
+
+    _fields_ = [
+        ("world_tan", ctypes.c_float),
+        ("half_width", ctypes.c_float), ("half_height", ctypes.c_float),
+        ("full_width", ctypes.c_float), ("full_height", ctypes.c_float),
+        ("origin", ctypes.c_float * 3), ("u", ctypes.c_float * 3),
+        ("v", ctypes.c_float * 3), ("w", ctypes.c_float * 3),
+        ("lens_radius", ctypes.c_double),
+    ]
+
+
+class EnvConfig(ctypes.Structure):
+    """rf_env_config."""
+
+    _fields_ = [
+        ("num_envs", ctypes.c_int), ("frame_height", ctypes.c_int),
+        ("samples_per_pixel", ctypes.c_int),
+        ("transformer", ctypes.c_int),
+        ("n_moves", ctypes.c_int),
+        ("moves", ctypes.c_double * 32),
+        ("limits", ctypes.c_float * 2),
+        ("jump_span", ctypes.c_float),
+        ("jump_threshold", ctypes.c_float),
+        ("max_steps", ctypes.c_int),
+        ("diverge_threshold", ctypes.c_float),
+        ("diverge_steps", ctypes.c_int),
+        ("rewarder", ctypes.c_int),
+        ("delta_reward", ctypes.c_float), ("delta_scale", ctypes.c_float),
+        ("stop_threshold", ctypes.c_float),
+        ("stop_reward", ctypes.c_double),
+        ("on_span", ctypes.c_float),
+        ("on_off", ctypes.c_double), ("on_delta", ctypes.c_double),
+        ("obs_mid", ctypes.c_float * 4), ("obs_scale", ctypes.c_float * 4),
+        ("init_low", ctypes.c_double * 2), ("init_high", ctypes.c_double * 2),
+        ("packing", ScenePacking),
+    ]
 
 _c_float_p = ctypes.POINTER(ctypes.c_float)
 _vp = ctypes.c_void_p
@@ -38,6 +82,7 @@ _SIGNATURES = {
     "rf_last_error": (ctypes.c_char_p, [_vp]),
     "rf_last_global_error": (ctypes.c_char_p, []),
     "rf_abi_version": (ctypes.c_int, []),
+    "rf_sizeof": (ctypes.c_int, [ctypes.c_int]),
     "rf_device_info": (ctypes.c_int, [_vp] + [ctypes.POINTER(ctypes.c_int)] * 4),
     "rf_launch_count": (ctypes.c_int64, [_vp]),
     "rf_rng_ensure": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_uint64, _vp]),
@@ -62,6 +107,18 @@ _SIGNATURES = {
     "rf_step_host": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp,
                                     _vp, _vp]),
     "rf_step_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    "rf_set_scene_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int,
+                                           ctypes.POINTER(ScenePacking), _vp]),
+    "rf_env_create": (ctypes.c_int, [_vp, ctypes.POINTER(EnvConfig), ctypes.POINTER(_vp)]),
+    "rf_env_destroy": (ctypes.c_int, [_vp]),
+    "rf_env_set_generator": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64),
+                                            ctypes.POINTER(ctypes.c_uint64)]),
+    "rf_env_get_generator": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64),
+                                            ctypes.POINTER(ctypes.c_uint64)]),
+    "rf_env_reset": (ctypes.c_int, [_vp, _vp, _vp]),
+    "rf_env_step": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp, _vp,
+                                   ctypes.POINTER(ctypes.c_int), _vp]),
+    "rf_env_export": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "rf_selftest": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int,
                                    ctypes.POINTER(ctypes.c_int64), _vp]),
     "rf_set_option": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
@@ -110,6 +167,11 @@ def load() -> ctypes.CDLL:
         if lib.rf_abi_version() != ABI_VERSION:
             raise NativeLibraryError(
                 f"{path} has ABI {lib.rf_abi_version()}, expected {ABI_VERSION}; rebuild it")
+        for which, struct in enumerate((ScenePacking, EnvConfig)):
+            if lib.rf_sizeof(which) != ctypes.sizeof(struct):
+                raise NativeLibraryError(
+                    f"{struct.__name__} is {ctypes.sizeof(struct)} bytes here but "
+                    f"{lib.rf_sizeof(which)} in {path}; rebuild it")
         _lib = lib
         return lib
 
@@ -268,6 +330,12 @@ class Context:
         self._check(self._lib.rf_step_device(self._handle, n, height, spp, _vp(d_focus),
                                              _stream_ptr(stream, self.device)))
 
+    def set_scene_device(self, n: int, d_targets: int, d_planes: int, stride: int,
+                         packing: ScenePacking, stream=None):
+        self._check(self._lib.rf_set_scene_device(self._handle, n, _vp(d_targets), _vp(d_planes),
+                                                  stride, ctypes.byref(packing),
+                                                  _stream_ptr(stream, self.device)))
+
     # ------------------------------------------------------------------- self-checks
     def selftest(self, which: int, arg: int = 0, stream=None) -> int:
         bad = ctypes.c_int64(-1)
@@ -292,6 +360,67 @@ class Context:
         self._check(self._lib.rf_measure_fp32_peak(self._handle, ctypes.byref(tflops),
                                                    ctypes.byref(mhz)))
         return tflops.value, mhz.value
+
+
+class DeviceEnv:
+    """One rf_env: the device-resident vector env bound to a context (= to one renderer)."""
+
+    _MASK64 = (1 << 64) - 1
+
+    def __init__(self, context: Context, config: EnvConfig):
+        self._context = context
+        self._lib = context._lib  # pylint: disable=protected-access
+        self.num_envs = config.num_envs
+        handle = _vp()
+        context._check(  # pylint: disable=protected-access
+            self._lib.rf_env_create(context._handle, ctypes.byref(config), ctypes.byref(handle)))
+        self._handle = handle
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.rf_env_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+    def _check(self, rc: int):
+        self._context._check(rc)  # pylint: disable=protected-access
+
+    def set_generator(self, state: int, inc: int):
+        """128-bit PCG64DXSM state and increment (numpy bit_generator.state['state'])."""
+
+        pair = ctypes.c_uint64 * 2
+        self._check(self._lib.rf_env_set_generator(
+            self._handle, pair(state >> 64, state & self._MASK64), pair(inc >> 64, inc & self._MASK64)))
+
+    def get_generator(self) -> tuple[int, int]:
+        state, inc = (ctypes.c_uint64 * 2)(), (ctypes.c_uint64 * 2)()
+        self._check(self._lib.rf_env_get_generator(self._handle, state, inc))
+        return (state[0] << 64) | state[1], (inc[0] << 64) | inc[1]
+
+    def reset(self, d_obs: int, stream=None):
+        self._check(self._lib.rf_env_reset(self._handle, _vp(d_obs),
+                                           _stream_ptr(stream, self._context.device)))
+
+    def step(self, d_actions: int, action_kind: int, d_obs: int, d_rewards: int, d_truncated: int,
+             stream=None) -> int:
+        resets = ctypes.c_int(0)
+        self._check(self._lib.rf_env_step(self._handle, _vp(d_actions), action_kind, _vp(d_obs),
+                                          _vp(d_rewards), _vp(d_truncated), ctypes.byref(resets),
+                                          _stream_ptr(stream, self._context.device)))
+        return resets.value
+
+    def export(self) -> dict:
+        states = numpy.empty((self.num_envs, 2), dtype=numpy.float32)
+        steps = numpy.empty(self.num_envs, dtype=numpy.int32)
+        diverging = numpy.empty(self.num_envs, dtype=numpy.int32)
+        self._check(self._lib.rf_env_export(self._handle, states.ctypes.data, steps.ctypes.data,
+                                            diverging.ctypes.data))
+        return {"states": states, "steps": steps, "diverging": diverging}
 
 
 _shared_contexts: dict[int, Context] = {}

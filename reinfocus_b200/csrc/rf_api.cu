@@ -1,6 +1,6 @@
 // C-ABI of the reinfocus_b200 hot path (include/reinfocus_b200.h). Host-side plumbing
 // only: context, buffers, launches. The kernels live in rf_rng.cuh / rf_tracer.cuh /
-// rf_focus.cuh. Built for sm_100a only (see reinfocus_b200/build.py).
+// rf_focus.cuh / rf_generic.cuh / rf_env.cuh. Built for sm_100a only (see reinfocus_b200/build.py).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -12,12 +12,13 @@
 #include <vector>
 
 #include "../../include/reinfocus_b200.h"
+#include "rf_env.cuh"
 #include "rf_focus.cuh"
 #include "rf_generic.cuh"
 #include "rf_rng.cuh"
 #include "rf_tracer.cuh"
 
-#define RF_ABI_VERSION 2
+#define RF_ABI_VERSION 3
 
 namespace {
 
@@ -324,6 +325,17 @@ __global__ void ffma_peak_kernel(float *out, int iters) {
 extern "C" {
 
 int rf_abi_version(void) { return RF_ABI_VERSION; }
+
+int rf_sizeof(int which) {
+    switch (which) {
+        case RF_SIZEOF_SCENE_PACKING:
+            return (int)sizeof(rf_scene_packing);
+        case RF_SIZEOF_ENV_CONFIG:
+            return (int)sizeof(rf_env_config);
+        default:
+            return -1;
+    }
+}
 
 const char *rf_last_global_error(void) { return g_global_error.c_str(); }
 
@@ -662,6 +674,275 @@ int rf_step_host(rf_ctx *ctx, int n, int H, int spp, const float *h_world, const
     if (int rc = rf_step_device(ctx, n, H, spp, ctx->d_focus, stream)) return rc;
     RF_CUDA(ctx, cudaMemcpyAsync(h_focus, ctx->d_focus, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
     RF_CUDA(ctx, cudaStreamSynchronize(s));
+    return RF_OK;
+}
+
+// ------------------------------------------------------------------- scene from the device
+
+int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float *d_planes, int stride,
+                        const rf_scene_packing *packing, void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_set_scene_device: ctx is NULL");
+    RF_REQUIRE(ctx, n > 0 && d_targets && d_planes && stride > 0 && packing,
+               "rf_set_scene_device: empty scene");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n > ctx->cap_world) {
+        RF_CUDA(ctx, cudaStreamSynchronize(s));
+        if (int rc = grow(ctx, (void **)&ctx->d_world, sizeof(float) * 2 * (size_t)n)) return rc;
+        ctx->cap_world = n;
+    }
+    if (n > ctx->cap_cam) {
+        RF_CUDA(ctx, cudaStreamSynchronize(s));
+        if (int rc = grow(ctx, (void **)&ctx->d_cam_dyn, sizeof(float) * 9 * (size_t)n)) return rc;
+        ctx->cap_cam = n;
+    }
+    rf::ScenePacking k{};
+    k.world_tan = packing->world_tan;
+    k.half_width = packing->half_width;
+    k.half_height = packing->half_height;
+    k.full_width = packing->full_width;
+    k.full_height = packing->full_height;
+    for (int i = 0; i < 3; ++i) {
+        k.origin[i] = ctx->origin[i] = packing->origin[i];
+        k.u[i] = ctx->u[i] = packing->u[i];
+        k.v[i] = ctx->v[i] = packing->v[i];
+        k.w[i] = packing->w[i];
+    }
+    ctx->lens_radius = packing->lens_radius;
+    rf::pack_scene_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, d_targets, d_planes, stride, k, ctx->d_world,
+                                                          ctx->d_cam_dyn);
+    ctx->launches++;
+    RF_CUDA(ctx, cudaGetLastError());
+    ctx->n_world = ctx->n_cam = n;
+    ctx->have_world = ctx->have_cam = true;
+    return RF_OK;
+}
+
+// ----------------------------------------------------------------------- device vector env
+
+struct rf_env {
+    rf_ctx *ctx = nullptr;
+    rf::EnvParams params{};
+    rf_scene_packing packing{};
+    int H = 0, spp = 0;
+    rf::EnvArrays arrays{};
+    double *d_focus_main = nullptr, *d_focus_reset = nullptr;
+    int *h_counters = nullptr;  // pinned [2]
+    cudaEvent_t counted = nullptr;
+    bool seeded = false, started = false;
+};
+
+int rf_env_destroy(rf_env *env) {
+    if (!env) return RF_OK;
+    DeviceGuard guard(env->ctx->device);
+    rf::EnvArrays &a = env->arrays;
+    cudaFree(a.states);
+    cudaFree(a.new_states);
+    cudaFree(a.reset_rank);
+    cudaFree(a.steps);
+    cudaFree(a.diverging);
+    cudaFree(a.last_gap);
+    cudaFree(a.old_obs);
+    cudaFree(a.old_plane);
+    cudaFree(a.generator);
+    cudaFree(a.counters);
+    cudaFree(env->d_focus_main);
+    cudaFree(env->d_focus_reset);
+    if (env->h_counters) cudaFreeHost(env->h_counters);
+    if (env->counted) cudaEventDestroy(env->counted);
+    delete env;
+    return RF_OK;
+}
+
+int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_env_create: ctx is NULL");
+    RF_REQUIRE(ctx, c && out, "rf_env_create: NULL argument");
+    RF_REQUIRE(ctx, c->num_envs > 0 && c->frame_height >= 2 && c->samples_per_pixel > 0,
+               "rf_env_create: num_envs, frame_height and samples_per_pixel must be positive");
+    RF_REQUIRE(ctx, c->transformer == RF_ENV_DISCRETE_MOVE || c->transformer == RF_ENV_CONTINUOUS_JUMP,
+               "rf_env_create: unknown transformer %d", c->transformer);
+    RF_REQUIRE(ctx, c->rewarder == RF_ENV_REWARD_STEPS || c->rewarder == RF_ENV_REWARD_JUMPS,
+               "rf_env_create: unknown rewarder %d", c->rewarder);
+    RF_REQUIRE(ctx, c->transformer != RF_ENV_DISCRETE_MOVE || (c->n_moves > 0 && c->n_moves <= rf::kEnvMaxMoves),
+               "rf_env_create: a discrete action set holds 1..%d moves", rf::kEnvMaxMoves);
+    RF_REQUIRE(ctx, c->diverge_steps > 0, "rf_env_create: diverge_steps must be positive");
+    DeviceGuard guard(ctx->device);
+    rf_env *env = new rf_env();
+    env->ctx = ctx;
+    env->H = c->frame_height;
+    env->spp = c->samples_per_pixel;
+    env->packing = c->packing;
+    rf::EnvParams &p = env->params;
+    p.n = c->num_envs;
+    p.transformer = c->transformer;
+    p.n_moves = c->n_moves;
+    for (int i = 0; i < rf::kEnvMaxMoves; ++i) p.moves[i] = i < c->n_moves ? c->moves[i] : 0.0;
+    p.limit_lo = c->limits[0];
+    p.limit_hi = c->limits[1];
+    p.jump_span = c->jump_span;
+    p.jump_threshold = c->jump_threshold;
+    p.max_steps = c->max_steps;
+    p.diverge_threshold = c->diverge_threshold;
+    p.diverge_steps = c->diverge_steps;
+    p.rewarder = c->rewarder;
+    p.delta_reward = c->delta_reward;
+    p.delta_scale = c->delta_scale;
+    p.stop_threshold = c->stop_threshold;
+    p.stop_reward = c->stop_reward;
+    p.on_span = c->on_span;
+    p.on_off = c->on_off;
+    p.on_delta = c->on_delta;
+    for (int i = 0; i < 4; ++i) {
+        p.obs_mid[i] = c->obs_mid[i];
+        p.obs_scale[i] = c->obs_scale[i];
+    }
+    for (int i = 0; i < 2; ++i) {
+        p.init_low[i] = c->init_low[i];
+        p.init_range[i] = c->init_high[i] - c->init_low[i];  // Generator.uniform: high - low in float64
+    }
+    const size_t n = (size_t)p.n;
+    rf::EnvArrays &a = env->arrays;
+    auto alloc = [&](void **ptr, size_t bytes) {
+        if (cudaMalloc(ptr, bytes) != cudaSuccess) return false;
+        return cudaMemset(*ptr, 0, bytes) == cudaSuccess;
+    };
+    const bool ok = alloc((void **)&a.states, sizeof(float) * 2 * n) &&
+                    alloc((void **)&a.new_states, sizeof(float) * 2 * n) &&
+                    alloc((void **)&a.reset_rank, sizeof(int) * n) && alloc((void **)&a.steps, sizeof(int) * n) &&
+                    alloc((void **)&a.diverging, sizeof(int) * n) && alloc((void **)&a.last_gap, sizeof(float) * n) &&
+                    alloc((void **)&a.old_obs, sizeof(float) * 2 * n) &&
+                    alloc((void **)&a.old_plane, sizeof(float) * n) &&
+                    alloc((void **)&a.generator, sizeof(uint64_t) * 4) &&
+                    alloc((void **)&a.counters, sizeof(int) * 2) &&
+                    alloc((void **)&env->d_focus_main, sizeof(double) * n) &&
+                    alloc((void **)&env->d_focus_reset, sizeof(double) * n) &&
+                    cudaMallocHost((void **)&env->h_counters, sizeof(int) * 2) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&env->counted, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        const cudaError_t err = cudaGetLastError();
+        rf_env_destroy(env);
+        return fail(ctx, RF_ERR_NOMEM, "rf_env_create: allocation failed: %s", cudaGetErrorString(err));
+    }
+    RF_CUDA(ctx, cudaDeviceSynchronize());
+    *out = env;
+    return RF_OK;
+}
+
+int rf_env_set_generator(rf_env *env, const uint64_t state[2], const uint64_t inc[2]) {
+    if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_set_generator: env is NULL");
+    rf_ctx *ctx = env->ctx;
+    RF_REQUIRE(ctx, state && inc, "rf_env_set_generator: NULL argument");
+    DeviceGuard guard(ctx->device);
+    const uint64_t words[4] = {state[0], state[1], inc[0], inc[1]};
+    RF_CUDA(ctx, cudaDeviceSynchronize());
+    RF_CUDA(ctx, cudaMemcpy(env->arrays.generator, words, sizeof(words), cudaMemcpyHostToDevice));
+    env->seeded = true;
+    return RF_OK;
+}
+
+int rf_env_get_generator(rf_env *env, uint64_t state[2], uint64_t inc[2]) {
+    if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_get_generator: env is NULL");
+    rf_ctx *ctx = env->ctx;
+    RF_REQUIRE(ctx, state && inc, "rf_env_get_generator: NULL argument");
+    DeviceGuard guard(ctx->device);
+    uint64_t words[4];
+    RF_CUDA(ctx, cudaDeviceSynchronize());
+    RF_CUDA(ctx, cudaMemcpy(words, env->arrays.generator, sizeof(words), cudaMemcpyDeviceToHost));
+    state[0] = words[0];
+    state[1] = words[1];
+    inc[0] = words[2];
+    inc[1] = words[3];
+    return RF_OK;
+}
+
+namespace {
+
+// the part of reset / step shared by both: restart scan, renders, observations
+int env_advance(rf_env *env, const void *d_actions, int action_kind, float *d_obs, double *d_rewards,
+                uint8_t *d_truncated, int *h_resets, bool reset_all, cudaStream_t s) {
+    rf_ctx *ctx = env->ctx;
+    const rf::EnvParams &p = env->params;
+    rf::env_pre_kernel<<<1, rf::kEnvPreThreads, 0, s>>>(p, env->arrays, d_actions, action_kind, reset_all ? 1 : 0);
+    ctx->launches++;
+    RF_CUDA(ctx, cudaGetLastError());
+    // the restart count is final before any rendering starts: fetch it behind the main
+    // render's launch so the host never stalls the GPU
+    RF_CUDA(ctx, cudaMemcpyAsync(env->h_counters, env->arrays.counters, sizeof(int) * 2,
+                                 cudaMemcpyDeviceToHost, s));
+    RF_CUDA(ctx, cudaEventRecord(env->counted, s));
+    if (!reset_all) {
+        if (int rc = rf_set_scene_device(ctx, p.n, env->arrays.states, env->arrays.states + 1, 2,
+                                         &env->packing, s))
+            return rc;
+        if (int rc = rf_step_device(ctx, p.n, env->H, env->spp, env->d_focus_main, s)) return rc;
+    }
+    RF_CUDA(ctx, cudaEventSynchronize(env->counted));
+    const int resets = env->h_counters[0];
+    if (env->h_counters[1]) {
+        int zero[2] = {0, 0};
+        cudaMemcpyAsync(env->arrays.counters, zero, sizeof(zero), cudaMemcpyHostToDevice, s);
+        cudaStreamSynchronize(s);
+        env->started = false;
+        return fail(ctx, RF_ERR_INVALID,
+                    "rf_env_step: an action index is outside the action set (the env must be reset)");
+    }
+    if (resets > 0) {
+        // the restarted envs render as batch positions 0..k-1 (reference
+        // state_observer.py:377-383 via vector_environment.py:144)
+        if (int rc = rf_set_scene_device(ctx, resets, env->arrays.new_states, env->arrays.new_states + 1, 2,
+                                         &env->packing, s))
+            return rc;
+        if (int rc = rf_step_device(ctx, resets, env->H, env->spp, env->d_focus_reset, s)) return rc;
+    }
+    rf::env_post_kernel<<<(p.n + 255) / 256, 256, 0, s>>>(p, env->arrays, env->d_focus_main, env->d_focus_reset,
+                                                         d_obs, d_rewards, d_truncated, reset_all ? 1 : 0);
+    ctx->launches++;
+    RF_CUDA(ctx, cudaGetLastError());
+    if (h_resets) *h_resets = resets;
+    return RF_OK;
+}
+
+}  // namespace
+
+int rf_env_reset(rf_env *env, float *d_obs, void *stream) {
+    if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_reset: env is NULL");
+    rf_ctx *ctx = env->ctx;
+    RF_REQUIRE(ctx, d_obs, "rf_env_reset: d_obs is NULL");
+    RF_REQUIRE(ctx, env->seeded, "rf_env_reset: set the generator first (rf_env_set_generator)");
+    DeviceGuard guard(ctx->device);
+    if (int rc = env_advance(env, nullptr, 0, d_obs, nullptr, nullptr, nullptr, true, (cudaStream_t)stream))
+        return rc;
+    env->started = true;
+    return RF_OK;
+}
+
+int rf_env_step(rf_env *env, const void *d_actions, int action_kind, float *d_obs, double *d_rewards,
+                uint8_t *d_truncated, int *h_resets, void *stream) {
+    if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_step: env is NULL");
+    rf_ctx *ctx = env->ctx;
+    RF_REQUIRE(ctx, env->started, "rf_env_step: reset the env first");
+    RF_REQUIRE(ctx, d_actions && d_obs && d_rewards && d_truncated, "rf_env_step: NULL argument");
+    const bool discrete = env->params.transformer == rf::kEnvDiscreteMove;
+    RF_REQUIRE(ctx,
+               discrete ? (action_kind == RF_ENV_ACTIONS_INT32 || action_kind == RF_ENV_ACTIONS_INT64)
+                        : action_kind == RF_ENV_ACTIONS_FLOAT32,
+               "rf_env_step: action kind %d does not fit the transformer", action_kind);
+    DeviceGuard guard(ctx->device);
+    return env_advance(env, d_actions, action_kind, d_obs, d_rewards, d_truncated, h_resets, false,
+                       (cudaStream_t)stream);
+}
+
+int rf_env_export(rf_env *env, float *h_states, int *h_steps, int *h_diverging) {
+    if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_export: env is NULL");
+    rf_ctx *ctx = env->ctx;
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)env->params.n;
+    RF_CUDA(ctx, cudaDeviceSynchronize());
+    if (h_states)
+        RF_CUDA(ctx, cudaMemcpy(h_states, env->arrays.states, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost));
+    if (h_steps) RF_CUDA(ctx, cudaMemcpy(h_steps, env->arrays.steps, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (h_diverging)
+        RF_CUDA(ctx, cudaMemcpy(h_diverging, env->arrays.diverging, sizeof(int) * n, cudaMemcpyDeviceToHost));
     return RF_OK;
 }
 

@@ -1,0 +1,302 @@
+// Env-step glue on the device: everything reference environments/vector_environment.py:75-164
+// does around the render + focus measure of a step, for the compositions the example envs
+// use (reference examples/custom_environments.py) - transformer, enders, Delta / Normalized
+// observers, rewarders, the initializer's generator and the same-step auto-reset - so that
+// states, observations and rewards never visit the host.
+//
+// The arithmetic follows the NumPy expressions of the reference classes operation by
+// operation, dtype promotion included (float32 unless noted; Python floats are weak under
+// NumPy 2, so they enter float32 expressions as float32). Every float operation is an
+// explicit round-to-nearest intrinsic: nothing here may be contracted into an FMA.
+#pragma once
+
+#include <cstdint>
+
+namespace rf {
+
+enum { kEnvDiscreteMove = 0, kEnvContinuousJump = 1 };
+enum { kEnvRewardSteps = 0, kEnvRewardJumps = 1 };
+enum { kEnvActionsInt32 = 0, kEnvActionsInt64 = 1, kEnvActionsFloat32 = 2 };
+constexpr int kEnvMaxMoves = 32;
+constexpr int kEnvPreThreads = 1024;
+
+struct EnvParams {
+    int n;
+    int transformer;             // kEnvDiscreteMove | kEnvContinuousJump
+    int n_moves;
+    double moves[kEnvMaxMoves];  // DiscreteMoveTransformer keeps its action set in float64
+    float limit_lo, limit_hi;
+    float jump_span;             // float32(limits[1] - limits[0]), the difference taken in Python
+    float jump_threshold;
+    int max_steps;               // TimeLimitEnder; <= 0: none
+    float diverge_threshold;     // DivergingEnder
+    int diverge_steps;
+    int rewarder;                // kEnvRewardSteps | kEnvRewardJumps
+    float delta_reward, delta_scale;  // DeltaRewarder
+    float stop_threshold;             // StoppedRewarder
+    double stop_reward;
+    float on_span;                    // OnTargetRewarder
+    double on_off, on_delta;
+    float obs_mid[4], obs_scale[4];   // NormalizedObserver
+    double init_low[2], init_range[2];  // RangedInitializer, one range per element
+};
+
+struct EnvArrays {
+    float *states;        // [n, 2]  target, focus plane
+    float *new_states;    // [n, 2]  first states of restarted episodes, by reset rank
+    int *reset_rank;      // [n]     position among this step's restarted envs, -1 if none
+    int *steps;           // [n]     TimeLimitEnder
+    int *diverging;       // [n]     DivergingEnder
+    float *last_gap;      // [n]
+    float *old_obs;       // [n, 2]  DeltaObserver: previous [focus plane, focus value]
+    float *old_plane;     // [n]     Delta / Stopped rewarder: previous focus plane
+    uint64_t *generator;  // [4]     PCG64DXSM state hi, lo, increment hi, lo
+    int *counters;        // [2]     number of restarted envs, invalid-action flag
+};
+
+// ------------------------------------------------------------------ numpy.random.PCG64DXSM
+
+using u128 = unsigned __int128;
+constexpr uint64_t kPcgCheapMultiplier = 0xda942042e4dd58b5ull;
+
+__device__ inline u128 pcg_make(uint64_t hi, uint64_t lo) { return ((u128)hi << 64) | lo; }
+
+// state after `delta` steps of state = state * M + inc (Brown's O(log delta) LCG skip)
+__device__ inline u128 pcg_advance(u128 state, u128 inc, uint64_t delta) {
+    u128 acc_mult = 1, acc_plus = 0, cur_mult = kPcgCheapMultiplier, cur_plus = inc;
+    while (delta > 0) {
+        if (delta & 1) {
+            acc_mult *= cur_mult;
+            acc_plus = acc_plus * cur_mult + cur_plus;
+        }
+        cur_plus = (cur_mult + 1) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1;
+    }
+    return acc_mult * state + acc_plus;
+}
+
+// Generator.random's double: DXSM output of the pre-step state, top 53 bits * 2^-53
+__device__ inline double pcg_next_double(u128 &state, u128 inc) {
+    uint64_t hi = (uint64_t)(state >> 64);
+    const uint64_t lo = (uint64_t)state | 1;
+    hi ^= hi >> 32;
+    hi *= kPcgCheapMultiplier;
+    hi ^= hi >> 48;
+    hi *= lo;
+    state = state * kPcgCheapMultiplier + inc;
+    return __dmul_rn((double)(hi >> 11), 1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------------- helpers
+
+// numpy.clip = minimum(maximum(x, lo), hi)
+__device__ inline float clip_f32(float x, float lo, float hi) {
+    x = x < lo ? lo : x;
+    return x > hi ? hi : x;
+}
+
+__device__ inline float env_gap(float target, float plane) { return fabsf(__fsub_rn(target, plane)); }
+
+__device__ inline float normalized(const EnvParams &p, int column, float value) {
+    // NormalizedObserver._normalize: clip((values - mid) / scale, -1, 1)
+    return clip_f32(__fdiv_rn(__fsub_rn(value, p.obs_mid[column]), p.obs_scale[column]), -1.0f, 1.0f);
+}
+
+// --------------------------------------------------------------------------- step, part 1
+//
+// One block walks the envs in chunks (an ordered scan is needed: restarted envs draw their
+// first states in env order from one generator, reference vector_environment.py:139 ->
+// state_initializer.py:63-69). Per env: transformer, ender step, is_truncated; restarted
+// envs get their rank and their new state. reset_all: every env restarts (env.reset()).
+__global__ void __launch_bounds__(kEnvPreThreads)
+env_pre_kernel(EnvParams p, EnvArrays a, const void *actions, int action_kind, int reset_all) {
+    __shared__ int warp_totals[kEnvPreThreads / 32];
+    __shared__ int chunk_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u128 gen_state = pcg_make(a.generator[0], a.generator[1]);
+    const u128 gen_inc = pcg_make(a.generator[2], a.generator[3]);
+    int base = 0;
+    bool invalid = false;
+
+    for (int chunk = 0; chunk < p.n; chunk += kEnvPreThreads) {
+        const int i = chunk + tid;
+        bool done = false;
+        if (i < p.n) {
+            if (reset_all) {
+                done = true;
+            } else {
+                float target = a.states[2 * i], plane = a.states[2 * i + 1];
+                if (p.transformer == kEnvDiscreteMove) {
+                    // DiscreteMoveTransformer: float32 state += float64 move, one rounding
+                    long long action = action_kind == kEnvActionsInt64
+                                           ? ((const long long *)actions)[i]
+                                           : (long long)((const int *)actions)[i];
+                    if (action < 0) action += p.n_moves;  // NumPy index wrap-around
+                    if (action < 0 || action >= p.n_moves) {
+                        invalid = true;
+                        action = 0;
+                    }
+                    plane = __double2float_rn(__dadd_rn((double)plane, p.moves[action]));
+                } else {
+                    // ContinuousJumpTransformer: ((a + 1) / 2) * (hi - lo) + lo, ignored when
+                    // closer than the stop threshold
+                    const float act = ((const float *)actions)[i];
+                    const float fraction = __fdiv_rn(__fadd_rn(act, 1.0f), 2.0f);
+                    const float destination =
+                        __fadd_rn(__fmul_rn(fraction, p.jump_span), p.limit_lo);
+                    if (fabsf(__fsub_rn(plane, destination)) > p.jump_threshold) plane = destination;
+                }
+                if (p.transformer == kEnvDiscreteMove) {
+                    target = clip_f32(target, p.limit_lo, p.limit_hi);
+                    plane = clip_f32(plane, p.limit_lo, p.limit_hi);
+                }
+                a.states[2 * i] = target;
+                a.states[2 * i + 1] = plane;
+                // ender.step, then is_truncated
+                const int steps = a.steps[i] + 1;
+                a.steps[i] = steps;
+                const float gap = env_gap(target, plane);
+                int diverging = a.diverging[i];
+                if (gap > __fadd_rn(a.last_gap[i], p.diverge_threshold)) a.diverging[i] = ++diverging;
+                a.last_gap[i] = gap;
+                done = (p.max_steps > 0 && steps >= p.max_steps) || diverging >= p.diverge_steps;
+            }
+        }
+        // ordered rank of the restarted envs
+        const unsigned ballot = __ballot_sync(0xffffffffu, done);
+        if (lane == 0) warp_totals[warp] = __popc(ballot);
+        __syncthreads();
+        if (warp == 0) {
+            int v = warp_totals[lane];
+#pragma unroll
+            for (int offset = 1; offset < 32; offset <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, v, offset);
+                if (lane >= offset) v += up;
+            }
+            warp_totals[lane] = v;  // inclusive
+            if (lane == 31) chunk_total = v;
+        }
+        __syncthreads();
+        const int rank = base + (warp > 0 ? warp_totals[warp - 1] : 0) +
+                         __popc(ballot & ((1u << lane) - 1));
+        if (i < p.n) a.reset_rank[i] = done ? rank : -1;
+        if (done) {
+            // RangedInitializer: uniform(low, high, size=(k, 2)) = low + range * double, in
+            // env-major order, rounded to float32 by astype
+            u128 state = pcg_advance(gen_state, gen_inc, 2ull * (uint64_t)rank);
+#pragma unroll
+            for (int element = 0; element < 2; ++element) {
+                const double unit = pcg_next_double(state, gen_inc);
+                a.new_states[2 * rank + element] = __double2float_rn(
+                    __dadd_rn(p.init_low[element], __dmul_rn(p.init_range[element], unit)));
+            }
+        }
+        base += chunk_total;
+        __syncthreads();
+    }
+    if (invalid) atomicExch(&a.counters[1], 1);
+    if (tid == 0) {
+        const u128 state = pcg_advance(gen_state, gen_inc, 2ull * (uint64_t)base);
+        a.generator[0] = (uint64_t)(state >> 64);
+        a.generator[1] = (uint64_t)state;
+        a.counters[0] = base;
+    }
+}
+
+// --------------------------------------------------------------------------- step, part 2
+//
+// focus_main[i]: focus value of env i's scene after the transformer; focus_reset[r]: focus
+// value of the first scene of the r-th restarted env (rendered as batch position r).
+// Observations, rewards (from the pre-reset observations, reference
+// vector_environment.py:128-130), then the restart bookkeeping of every strategy.
+__global__ void env_post_kernel(EnvParams p, EnvArrays a, const double *focus_main,
+                                const double *focus_reset, float *obs, double *rewards,
+                                uint8_t *truncated, int reset_all) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const int rank = a.reset_rank[i];
+    float out[4];
+    if (!reset_all) {
+        const float target = a.states[2 * i], plane = a.states[2 * i + 1];
+        // DeltaObserver over [IndexedElementObserver(plane), FocusObserver]; hstack casts the
+        // float64 focus value to float32
+        const float value = __double2float_rn(focus_main[i]);
+        const float raw[4] = {plane, value, __fsub_rn(plane, a.old_obs[2 * i]),
+                              __fsub_rn(value, a.old_obs[2 * i + 1])};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) out[c] = normalized(p, c, raw[c]);
+        a.old_obs[2 * i] = plane;
+        a.old_obs[2 * i + 1] = value;
+
+        const float moved = fabsf(__fsub_rn(plane, a.old_plane[i]));
+        a.old_plane[i] = plane;
+        const double on_target =
+            __dadd_rn(env_gap(target, plane) < p.on_span ? p.on_delta : 0.0, p.on_off);
+        double reward;
+        if (p.rewarder == kEnvRewardSteps) {
+            // (DeltaRewarder + ObservationRewarder(1)) + OnTargetRewarder: float32 + float32,
+            // then float64 because bool * Python float is float64
+            const float travel = __fdiv_rn(__fmul_rn(moved, p.delta_reward), p.delta_scale);
+            reward = __dadd_rn((double)__fadd_rn(travel, out[1]), on_target);
+        } else {
+            // ObservationRewarder(1) + (StoppedRewarder * OnTargetRewarder)
+            const double stopped = moved < p.stop_threshold ? p.stop_reward : 0.0;
+            reward = __dadd_rn((double)out[1], __dmul_rn(stopped, on_target));
+        }
+        rewards[i] = reward;
+        truncated[i] = rank >= 0;
+    }
+    if (rank >= 0) {
+        // same-step auto-reset (reference vector_environment.py:137-151)
+        const float target = a.new_states[2 * rank], plane = a.new_states[2 * rank + 1];
+        a.states[2 * i] = target;
+        a.states[2 * i + 1] = plane;
+        a.steps[i] = 0;
+        a.diverging[i] = 0;
+        a.last_gap[i] = env_gap(target, plane);
+        const float value = __double2float_rn(focus_reset[rank]);
+        a.old_obs[2 * i] = plane;
+        a.old_obs[2 * i + 1] = value;
+        a.old_plane[i] = plane;
+        out[0] = normalized(p, 0, plane);
+        out[1] = normalized(p, 1, value);
+        out[2] = normalized(p, 2, 0.0f);  // DeltaObserver emits zero changes on reset
+        out[3] = normalized(p, 3, 0.0f);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) obs[4 * i + c] = out[c];
+}
+
+// ------------------------------------------------------------------- scene packing (a1, a2)
+
+struct ScenePacking {
+    float world_tan;                       // float32(tan(radians(r_size / 2)))
+    float half_width, half_height;         // float32(hw), float32(hh)
+    float full_width, full_height;         // float32(2 * hw), float32(2 * hh)
+    float origin[3], u[3], v[3], w[3];
+};
+
+// FastWorlds._make_device_data (reference graphics/world.py:107-123) and
+// FastCameras._make_device_data (reference graphics/camera.py:144-179) from device-resident
+// target / focus-plane positions, same float32 operations in the same order
+__global__ void pack_scene_kernel(int n, const float *targets, const float *planes, int stride,
+                                  ScenePacking k, float *world, float *cam_dyn) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float target = targets[(size_t)i * stride], f = planes[(size_t)i * stride];
+    world[2 * i] = __fmul_rn(target, k.world_tan);
+    world[2 * i + 1] = -target;
+    const float wide = __fmul_rn(k.half_width, f), tall = __fmul_rn(k.half_height, f);
+    const float full_wide = __fmul_rn(k.full_width, f), full_tall = __fmul_rn(k.full_height, f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float total = __fadd_rn(__fadd_rn(__fmul_rn(k.u[c], wide), __fmul_rn(k.v[c], tall)),
+                                      __fmul_rn(k.w[c], f));
+        cam_dyn[9 * i + c] = __fsub_rn(k.origin[c], total);
+        cam_dyn[9 * i + 3 + c] = __fmul_rn(k.u[c], full_wide);
+        cam_dyn[9 * i + 6 + c] = __fmul_rn(k.v[c], full_tall);
+    }
+}
+
+}  // namespace rf

@@ -1,0 +1,273 @@
+"""Vector env whose whole step stays on the GPU.
+
+``VectorEnvironment`` (reference environments/vector_environment.py:75-164) runs its strategy
+objects in NumPy on the host and only the render + focus measure on the GPU.
+``DeviceVectorEnvironment`` takes the SAME strategy objects, reads their parameters and runs
+their arithmetic in two small CUDA kernels around the render (rf_env_step), so states,
+observations and rewards live in device memory and a policy on the GPU can act on them
+without a host round trip. Sequences are bit-identical to ``VectorEnvironment`` driven by the
+same generator (tests/test_gpu_parity.py).
+
+Only the compositions of the example envs are understood (anything else raises
+``NotImplementedError`` - use ``VectorEnvironment`` for it):
+
+* state ``[target, focus plane]``;
+* transformer ``DiscreteMoveTransformer`` or ``ContinuousJumpTransformer`` on the focus plane;
+* ender ``DivergingEnder`` on (target, focus plane), optionally ``TimeLimitEnder | ...``;
+* observer ``NormalizedObserver(DeltaObserver([IndexedElementObserver(focus plane),
+  FocusObserver], include_original=True, ...))``;
+* rewarder ``DeltaRewarder + ObservationRewarder(1) + OnTargetRewarder`` or
+  ``ObservationRewarder(1) + StoppedRewarder * OnTargetRewarder``;
+* initializer ``RangedInitializer`` with one range per element and a PCG64DXSM generator.
+"""
+
+from typing import Any
+
+import numpy
+
+from reinfocus_b200 import _lib
+from reinfocus_b200 import gym_compat
+from reinfocus_b200.environments import episode_ender
+from reinfocus_b200.environments import episode_rewarder
+from reinfocus_b200.environments import state_initializer
+from reinfocus_b200.environments import state_observer
+from reinfocus_b200.environments import state_transformer
+
+TARGET, FOCUS_PLANE = 0, 1
+
+
+def _unsupported(what: str):
+    raise NotImplementedError(
+        f"DeviceVectorEnvironment does not understand this {what}; use VectorEnvironment")
+
+
+def _f32(value) -> float:
+    return float(numpy.float32(value))
+
+
+def _read_transformer(transformer, config: _lib.EnvConfig):
+    # pylint: disable=protected-access
+    if transformer._move_index != FOCUS_PLANE:
+        _unsupported("transformer (it must move the focus plane)")
+    config.limits[0], config.limits[1] = (_f32(limit) for limit in transformer._limits)
+    if isinstance(transformer, state_transformer.DiscreteMoveTransformer):
+        moves = numpy.asarray(transformer._action_set, dtype=numpy.float64)
+        if len(moves) > 32:
+            _unsupported("transformer (more than 32 moves)")
+        config.transformer = _lib.ENV_DISCRETE_MOVE
+        config.n_moves = len(moves)
+        for i, move in enumerate(moves):
+            config.moves[i] = float(move)
+    elif isinstance(transformer, state_transformer.ContinuousJumpTransformer):
+        config.transformer = _lib.ENV_CONTINUOUS_JUMP
+        config.jump_span = _f32(transformer._limits[1] - transformer._limits[0])
+        config.jump_threshold = _f32(transformer._stop_threshold)
+    else:
+        _unsupported("transformer")
+
+
+def _read_ender(ender, config: _lib.EnvConfig):
+    # pylint: disable=protected-access
+    config.max_steps = 0
+    if isinstance(ender, episode_ender.OpEnder):
+        if ender._op is not numpy.bitwise_or:
+            _unsupported("ender (only | is supported)")
+        pair = (ender._l_ender, ender._r_ender)
+        limits = [e for e in pair if isinstance(e, episode_ender.TimeLimitEnder)]
+        others = [e for e in pair if not isinstance(e, episode_ender.TimeLimitEnder)]
+        if len(limits) != 1 or len(others) != 1:
+            _unsupported("ender")
+        config.max_steps = int(limits[0]._max_steps)
+        ender = others[0]
+    if not isinstance(ender, episode_ender.DivergingEnder):
+        _unsupported("ender")
+    if tuple(ender._check_indices) not in ((TARGET, FOCUS_PLANE), (FOCUS_PLANE, TARGET)):
+        _unsupported("ender (it must compare target and focus plane)")
+    config.diverge_threshold = _f32(ender._threshold)
+    config.diverge_steps = int(ender._early_end_steps)
+
+
+def _read_on_target(rewarder, config: _lib.EnvConfig):
+    # pylint: disable=protected-access
+    if not isinstance(rewarder, episode_rewarder.OnTargetRewarder) or tuple(
+            rewarder._check_indices) not in ((TARGET, FOCUS_PLANE), (FOCUS_PLANE, TARGET)):
+        _unsupported("rewarder")
+    config.on_span = _f32(rewarder._span)
+    config.on_off = float(rewarder._off)
+    config.on_delta = float(rewarder._delta)
+
+
+def _is_focus_reward(rewarder) -> bool:
+    # pylint: disable=protected-access
+    return (isinstance(rewarder, episode_rewarder.ObservationRewarder)
+            and rewarder._reward_observation_index == 1)
+
+
+def _read_rewarder(rewarder, config: _lib.EnvConfig):
+    # pylint: disable=protected-access
+    def op(node, ufunc):
+        return isinstance(node, episode_rewarder.OpRewarder) and node._op is ufunc
+
+    if op(rewarder, numpy.add) and op(rewarder._l_rewarder, numpy.add):
+        # (DeltaRewarder + ObservationRewarder(1)) + OnTargetRewarder
+        delta, focus = rewarder._l_rewarder._l_rewarder, rewarder._l_rewarder._r_rewarder
+        if not (isinstance(delta, episode_rewarder.DeltaRewarder)
+                and delta._check_index == FOCUS_PLANE and _is_focus_reward(focus)):
+            _unsupported("rewarder")
+        config.rewarder = _lib.ENV_REWARD_STEPS
+        config.delta_reward = _f32(delta._reward)
+        config.delta_scale = _f32(delta._scale)
+        _read_on_target(rewarder._r_rewarder, config)
+    elif op(rewarder, numpy.add) and op(rewarder._r_rewarder, numpy.multiply):
+        # ObservationRewarder(1) + (StoppedRewarder * OnTargetRewarder)
+        stopped = rewarder._r_rewarder._l_rewarder
+        if not (_is_focus_reward(rewarder._l_rewarder)
+                and isinstance(stopped, episode_rewarder.StoppedRewarder)
+                and stopped._check_index == FOCUS_PLANE):
+            _unsupported("rewarder")
+        config.rewarder = _lib.ENV_REWARD_JUMPS
+        config.stop_threshold = _f32(stopped._threshold)
+        config.stop_reward = float(stopped._reward)
+        _read_on_target(rewarder._r_rewarder._r_rewarder, config)
+    else:
+        _unsupported("rewarder")
+
+
+def _read_observer(observer, config: _lib.EnvConfig):
+    # pylint: disable=protected-access
+    if not (isinstance(observer, state_observer.NormalizedObserver) and len(observer._observers) == 1):
+        _unsupported("observer")
+    delta = observer._observers[0]
+    if not (isinstance(delta, state_observer.DeltaObserver) and delta._include_original
+            and len(delta._observers) == 2):
+        _unsupported("observer")
+    plane, focus = delta._observers
+    if not (isinstance(plane, state_observer.IndexedElementObserver)
+            and plane._element_index == FOCUS_PLANE
+            and isinstance(focus, state_observer.FocusObserver)
+            and focus._target_index == TARGET and focus._focus_plane_index == FOCUS_PLANE):
+        _unsupported("observer")
+    assert observer._mid.dtype == numpy.float32 and observer._scale.dtype == numpy.float32
+    for i in range(4):
+        config.obs_mid[i] = float(observer._mid[i])
+        config.obs_scale[i] = float(observer._scale[i])
+    config.frame_height = int(focus._frame_height)
+    return focus._renderer
+
+
+def _read_initializer(initializer, config: _lib.EnvConfig):
+    # pylint: disable=protected-access
+    if not (isinstance(initializer, state_initializer.RangedInitializer)
+            and len(initializer._ranges) == 2
+            and all(len(options) == 1 for options in initializer._ranges)):
+        _unsupported("initializer")
+    generator = initializer._generator
+    if generator.bit_generator.state["bit_generator"] != "PCG64DXSM":
+        _unsupported("initializer (its generator must be a PCG64DXSM)")
+    for i, options in enumerate(initializer._ranges):
+        config.init_low[i], config.init_high[i] = (float(end) for end in options[0])
+    return generator
+
+
+class DeviceVectorEnvironment(gym_compat.VectorEnv):
+    # pylint: disable=too-many-instance-attributes
+    """``VectorEnvironment`` with the step on the GPU. ``reset`` / ``step`` return torch CUDA
+    tensors: observations float32 (n, 4), rewards float64 (n,), terminated / truncated bool
+    (n,). ``step`` takes actions as a torch CUDA tensor (int32 / int64 for discrete moves,
+    float32 for jumps) or anything ``numpy.asarray`` understands (copied to the GPU).
+
+    The initializer's NumPy generator is read once, at construction: from then on the env
+    owns the stream on the device (``generator_state`` returns where it stands)."""
+
+    metadata = {"render_modes": []}
+
+    def __init__(self, ender, initializer, observer, rewarder, transformer, num_envs: int = 2):
+        # pylint: disable=too-many-arguments
+        import torch
+
+        super().__init__()
+        self.num_envs = num_envs
+        self.action_space = transformer.action_space
+        self.observation_space = observer.observation_space
+        self.single_action_space = transformer.single_action_space
+        self.single_observation_space = observer.single_observation_space
+        self.render_mode = None
+
+        config = _lib.EnvConfig()
+        config.num_envs = num_envs
+        _read_transformer(transformer, config)
+        _read_ender(ender, config)
+        _read_rewarder(rewarder, config)
+        renderer = _read_observer(observer, config)
+        generator = _read_initializer(initializer, config)
+        config.samples_per_pixel = renderer.samples_per_pixel
+        config.packing = renderer.scene_packing()
+
+        self._renderer = renderer
+        self._discrete = config.transformer == _lib.ENV_DISCRETE_MOVE
+        self._device = torch.device(f"cuda:{renderer.context.device}")
+        self._env = _lib.DeviceEnv(renderer.context, config)
+        words = generator.bit_generator.state["state"]
+        self._env.set_generator(int(words["state"]), int(words["inc"]))
+        self._started = False
+        self.last_resets = 0
+
+    # ------------------------------------------------------------------------ gym surface
+    def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
+        import torch
+
+        super().reset(seed=seed)
+        observations = torch.empty((self.num_envs, 4), dtype=torch.float32, device=self._device)
+        self._renderer.scene_overwritten()
+        self._env.reset(observations.data_ptr())
+        self._started = True
+        return observations, {}
+
+    def step(self, actions):
+        import torch
+
+        assert self._started, "reset the env first"
+        actions, kind = self._device_actions(actions)
+        observations = torch.empty((self.num_envs, 4), dtype=torch.float32, device=self._device)
+        rewards = torch.empty((self.num_envs,), dtype=torch.float64, device=self._device)
+        truncated = torch.empty((self.num_envs,), dtype=torch.bool, device=self._device)
+        terminated = torch.zeros((self.num_envs,), dtype=torch.bool, device=self._device)
+        self._renderer.scene_overwritten()
+        self.last_resets = self._env.step(actions.data_ptr(), kind, observations.data_ptr(),
+                                          rewards.data_ptr(), truncated.data_ptr())
+        return observations, rewards, terminated, truncated, {}
+
+    def close(self, **kwargs):
+        self._env.close()
+
+    # ------------------------------------------------------------------------- inspection
+    def generator_state(self) -> tuple[int, int]:
+        """(state, increment) of the PCG64DXSM stream the restarts draw from."""
+
+        return self._env.get_generator()
+
+    def export_state(self) -> dict:
+        """Host copies of the states and ender counters (tests, checkpoints)."""
+
+        return self._env.export()
+
+    # ---------------------------------------------------------------------------- helpers
+    def _device_actions(self, actions):
+        import torch
+
+        if not isinstance(actions, torch.Tensor):
+            actions = numpy.asarray(actions).reshape(-1)
+            if self._discrete:
+                actions = actions.astype(numpy.int64, copy=False)
+            else:
+                assert actions.dtype == numpy.float32, (
+                    "continuous actions must be float32 (the jump arithmetic takes their dtype)")
+            actions = torch.from_numpy(numpy.ascontiguousarray(actions)).to(self._device)
+        actions = actions.reshape(-1).contiguous()
+        assert actions.is_cuda and actions.shape[0] == self.num_envs, "one action per env"
+        if self._discrete:
+            kinds = {torch.int32: _lib.ENV_ACTIONS_INT32, torch.int64: _lib.ENV_ACTIONS_INT64}
+            assert actions.dtype in kinds, "discrete actions must be int32 or int64"
+            return actions, kinds[actions.dtype]
+        assert actions.dtype == torch.float32, "continuous actions must be float32"
+        return actions, _lib.ENV_ACTIONS_FLOAT32

@@ -4,6 +4,7 @@ All cameras share position, orientation, aperture and field of view; only the fo
 distance differs per env. The per-env part is float32 [n, 3, 3] = (lower left corner,
 horizontal, vertical); origin, u, v and the float64 lens radius are passed by value."""
 
+import ctypes
 import math
 
 import numpy
@@ -80,6 +81,19 @@ class FastCameras(device_data.DeviceData):
         """(origin, u, v, lens radius) passed to the kernel by value."""
 
         return self._look_from, self._u, self._v, float(self._half_aperture)
+
+    @property
+    def packing_constants(self):
+        """The float32 constants ``_make_device_data`` multiplies with, in the field order of
+        rf_scene_packing after ``world_tan``: half width / height, full width / height,
+        origin, u, v, w and the (float64) lens radius."""
+
+        f32 = numpy.float32
+        vec = lambda values: (ctypes.c_float * 3)(*[float(f32(x)) for x in values])
+        return (float(f32(self._half_width)), float(f32(self._half_height)),
+                float(f32(2.0 * self._half_width)), float(f32(2.0 * self._half_height)),
+                vec(self._look_from), vec(self._u), vec(self._v), vec(self._w),
+                float(self._half_aperture))
 
     def _make_device_data(self, data: NDArray[numpy.float32]) -> NDArray[numpy.float32]:
         # reference camera.py:132-179, one env at a time; vectorised here with the same

@@ -154,6 +154,38 @@ class FastRenderer:
         self._ctx.step_device(n, frame_height, self._samples_per_pixel, out.data_ptr())
         return out
 
+    def scene_packing(self) -> _lib.ScenePacking:
+        """The constants of the host packing (FastWorlds / FastCameras ._make_device_data)
+        for rf_set_scene_device, which does that packing on the GPU."""
+
+        return _lib.ScenePacking(self._worlds.packing_constant, *self._cameras.packing_constants)
+
+    def scene_overwritten(self):
+        """Tells the renderer that someone (rf_set_scene_device, a device env) replaced the
+        scene inside its context: the next host-side render uploads again."""
+
+        self._uploaded_world = -1
+        self._uploaded_cameras = -1
+
+    def step_focus_device(self, targets, focus_planes, frame_height: int = 300):
+        """``step_focus`` for positions that already live on the GPU: float32 CUDA tensors
+        (n,) in (any stride), float64 CUDA tensor (n,) out, no host copies. Scene packing
+        (reference world.py:107-123, camera.py:132-179) runs on the device."""
+
+        import torch
+
+        assert targets.is_cuda and focus_planes.is_cuda, "device tensors expected"
+        assert targets.dtype == torch.float32 and focus_planes.dtype == torch.float32
+        assert targets.dim() == 1 and targets.shape == focus_planes.shape
+        assert targets.stride(0) == focus_planes.stride(0)
+        n = targets.shape[0]
+        out = torch.empty((n,), dtype=torch.float64, device=targets.device)
+        self._ctx.set_scene_device(n, targets.data_ptr(), focus_planes.data_ptr(),
+                                   targets.stride(0), self.scene_packing())
+        self.scene_overwritten()
+        self._ctx.step_device(n, frame_height, self._samples_per_pixel, out.data_ptr())
+        return out
+
     def step_focus(self, targets: Collection[float], focus_planes: Collection[float],
                    frame_height: int = 300) -> NDArray[numpy.float64]:
         """One FocusObserver.observe (reference state_observer.py:377-383) in a single

@@ -47,6 +47,12 @@ class FastWorlds(device_data.DeviceData):
         # treats as weak: the product is a float32 multiply by float32(tan).
         self._tan = numpy.float32(math.tan(math.radians(r_size / 2)))
 
+    @property
+    def packing_constant(self) -> float:
+        """float32(tan(radians(r_size / 2))), the factor of ``_make_device_data``."""
+
+        return float(self._tan)
+
     def _make_device_data(self, data: NDArray[numpy.float32]) -> NDArray[numpy.float32]:
         packed = numpy.empty((len(data), 2), dtype=numpy.float32)
         packed[:, 0] = data * self._tan

@@ -138,3 +138,70 @@ def test_sb3_adapter_follows_the_vec_env_protocol(modules):
     if not vector_shim.HAVE_SB3:
         marker = object()
         assert vector_shim.rewrapper(marker) is marker
+
+
+def test_device_env_refuses_compositions_it_does_not_implement(modules):
+    """DeviceVectorEnvironment reads the parameters of a fixed menu of strategy compositions;
+    anything else must raise instead of being approximated."""
+
+    from reinfocus_b200 import _lib
+    from reinfocus_b200.environments import device_vector_environment as dve
+
+    m = modules
+    config = _lib.EnvConfig()
+    time_limit = m.episode_ender.TimeLimitEnder(2, 20)
+    diverging = m.episode_ender.DivergingEnder(2, (0, 1), 0.125, early_end_steps=3)
+    dve._read_ender(time_limit | diverging, config)
+    assert (config.max_steps, config.diverge_steps, config.diverge_threshold) == (20, 3, 0.125)
+    dve._read_ender(diverging, config)
+    assert config.max_steps == 0
+    for ender in (time_limit & diverging, time_limit, m.episode_ender.OnTargetEnder(2, (0, 1), 0.4),
+                  m.episode_ender.DivergingEnder(2, (0, 0), 0.1)):
+        with pytest.raises(NotImplementedError):
+            dve._read_ender(ender, config)
+
+    rewarders = m.episode_rewarder
+    steps = (rewarders.DeltaRewarder(1, 0.5) + rewarders.ObservationRewarder(1)
+             + rewarders.OnTargetRewarder((0, 1), 0.25))
+    dve._read_rewarder(steps, config)
+    assert (config.rewarder, config.delta_reward, config.delta_scale) == (_lib.ENV_REWARD_STEPS, -1.0, 0.5)
+    assert (config.on_span, config.on_off, config.on_delta) == (0.25, 0.0, 1.0)
+    jumps = rewarders.ObservationRewarder(1) + rewarders.StoppedRewarder(1, 0.125) * rewarders.OnTargetRewarder(
+        (0, 1), 0.25)
+    dve._read_rewarder(jumps, config)
+    assert (config.rewarder, config.stop_threshold, config.stop_reward) == (_lib.ENV_REWARD_JUMPS, 0.125, 1.0)
+    for rewarder in (rewarders.DistanceRewarder((0, 1), 5.0), rewarders.ObservationRewarder(1),
+                     rewarders.DeltaRewarder(0, 0.5) + rewarders.ObservationRewarder(1)
+                     + rewarders.OnTargetRewarder((0, 1), 0.25),
+                     rewarders.DeltaRewarder(1, 0.5) + rewarders.ObservationRewarder(0)
+                     + rewarders.OnTargetRewarder((0, 1), 0.25)):
+        with pytest.raises(NotImplementedError):
+            dve._read_rewarder(rewarder, config)
+
+    transformers = m.state_transformer
+    dve._read_transformer(transformers.DiscreteMoveTransformer(2, 1, (5.0, 10.0), [-1.0, 0.0, 1.0]), config)
+    assert (config.transformer, config.n_moves, list(config.moves[:3])) == (0, 3, [-1.0, 0.0, 1.0])
+    dve._read_transformer(transformers.ContinuousJumpTransformer(2, 1, (5.0, 10.0), 0.125), config)
+    assert (config.transformer, config.jump_span, config.jump_threshold) == (1, 5.0, 0.125)
+    for transformer in (transformers.DiscreteMoveTransformer(2, 0, (5.0, 10.0), [0.0]),
+                        transformers.ContinuousMoveTransformer(2, 1, (5.0, 10.0), 1.0),
+                        transformers.DiscreteMoveTransformer(2, 1, (5.0, 10.0), numpy.zeros(33))):
+        with pytest.raises(NotImplementedError):
+            dve._read_transformer(transformer, config)
+
+    initializers = m.state_initializer
+    generator = dve._read_initializer(initializers.RangedInitializer([[(5.0, 10.0)]] * 2, seed=3), config)
+    assert generator.bit_generator.state["bit_generator"] == "PCG64DXSM"
+    assert list(config.init_low) == [5.0, 5.0] and list(config.init_high) == [10.0, 10.0]
+    for initializer in (initializers.RangedInitializer([[(5.0, 6.0), (8.0, 9.0)], [(5.0, 10.0)]]),
+                        initializers.RangedInitializer([[(5.0, 10.0)]] * 3),
+                        initializers.FixedInitializer(numpy.zeros((4, 2))),
+                        initializers.RangedInitializer(
+                            [[(5.0, 10.0)]] * 2, generator=numpy.random.Generator(numpy.random.PCG64(1)))):
+        with pytest.raises(NotImplementedError):
+            dve._read_initializer(initializer, config)
+
+    focus_cls = gen_golden_env.make_analytic_observer(modules.state_observer)
+    env, _, _ = gen_golden_env.sim_cases()["discrete_vector"](modules, focus_cls)
+    with pytest.raises(NotImplementedError):  # the focus value must come from FocusObserver
+        dve._read_observer(env._observer, config)

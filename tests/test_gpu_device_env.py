@@ -1,0 +1,209 @@
+"""GPU tests of the device-resident vector env and of the on-device
+scene packing (a1, a2): both must be bit-identical to the host classes, which the CPU suite
+pins to the reference's own classes and the other GPU tests pin to the reference's numba-CUDA
+run."""
+
+import os
+
+import numpy
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+ENDS = (5.0, 10.0)
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    return torch
+
+
+def _generator(seed):
+    return numpy.random.Generator(numpy.random.PCG64DXSM(seed))
+
+
+def _strategies(num_envs, renderer, seed, frame_height, kind="steps", max_steps=20):
+    from reinfocus_b200.environments import (episode_ender, episode_rewarder, state_initializer,
+                                             state_observer, state_transformer)
+
+    observer = state_observer.NormalizedObserver(state_observer.DeltaObserver(
+        [state_observer.IndexedElementObserver(num_envs, 1, *ENDS),
+         state_observer.FocusObserver(num_envs, 0, 1, ENDS, renderer, frame_height)],
+        True, numpy.array([5.0, numpy.nan])))
+    ender = episode_ender.DivergingEnder(num_envs, (0, 1), 0.125, early_end_steps=3)
+    if max_steps:
+        ender = episode_ender.TimeLimitEnder(num_envs, max_steps) | ender
+    if kind == "steps":
+        moves = 5.0 / 2.0 ** numpy.arange(6)
+        transformer = state_transformer.DiscreteMoveTransformer(
+            num_envs, 1, ENDS, numpy.concatenate([-moves, [0], moves[::-1]]))
+        rewarder = (episode_rewarder.DeltaRewarder(1, 0.5) + episode_rewarder.ObservationRewarder(1)
+                    + episode_rewarder.OnTargetRewarder((0, 1), 0.25))
+    else:
+        transformer = state_transformer.ContinuousJumpTransformer(num_envs, 1, ENDS, 0.125)
+        rewarder = (episode_rewarder.ObservationRewarder(1)
+                    + episode_rewarder.StoppedRewarder(1, 0.125)
+                    * episode_rewarder.OnTargetRewarder((0, 1), 0.25))
+    return {"ender": ender,
+            "initializer": state_initializer.RangedInitializer([[ENDS]] * 2, generator=_generator(seed)),
+            "observer": observer, "rewarder": rewarder, "transformer": transformer}
+
+
+def _pair(num_envs, seed, frame_height=300, spp=100, **kwargs):
+    """The host env and the device env over the same strategies, each with its own fresh
+    renderer (= its own seed-0 RNG state cache) and its own copy of the generator."""
+
+    from reinfocus_b200.environments import device_vector_environment, vector_environment
+    from reinfocus_b200.graphics import render
+
+    host = vector_environment.VectorEnvironment(
+        **_strategies(num_envs, render.FastRenderer(samples_per_pixel=spp), seed, frame_height, **kwargs),
+        visualizer=None, num_envs=num_envs)
+    device = device_vector_environment.DeviceVectorEnvironment(
+        **_strategies(num_envs, render.FastRenderer(samples_per_pixel=spp), seed, frame_height, **kwargs),
+        num_envs=num_envs)
+    return host, device
+
+
+def _assert_same_rollout(host, device, actions):
+    want_obs, _ = host.reset()
+    got_obs, _ = device.reset()
+    assert got_obs.dtype.is_floating_point and got_obs.is_cuda
+    numpy.testing.assert_array_equal(got_obs.cpu().numpy(), want_obs)
+    resets = 0
+    for step, step_actions in enumerate(actions):
+        want = host.step(step_actions)
+        got = device.step(step_actions)
+        for name, w, g in zip(("obs", "rewards", "terminated", "truncated"), want, got):
+            g = g.cpu().numpy()
+            assert g.dtype == w.dtype, (name, g.dtype, w.dtype)
+            numpy.testing.assert_array_equal(g, w, err_msg=f"{name} at step {step}")
+        assert device.last_resets == int(want[3].sum())
+        resets += device.last_resets
+    exported = device.export_state()
+    numpy.testing.assert_array_equal(exported["states"], host._state)
+    host_generator = host._initializer._generator.bit_generator.state["state"]
+    assert device.generator_state() == (host_generator["state"], host_generator["inc"])
+    numpy.testing.assert_array_equal(device._renderer.context.rng_export(0, 4096),
+                                     host._observer._observers[0]._observers[1]._renderer.context.rng_export(0, 4096))
+    return resets
+
+
+def test_discrete_device_env_equals_host_env(torch):
+    """8 envs x 60 steps of the DiscreteSteps composition at the real frame size: every
+    observation, reward and truncation, the states, the initializer's generator and the
+    renderer's RNG states end up identical."""
+
+    host, device = _pair(8, seed=31)
+    actions = numpy.random.Generator(numpy.random.PCG64(3)).integers(0, 13, (60, 8))
+    assert _assert_same_rollout(host, device, actions) > 8
+
+
+def test_device_env_matches_reference_numba_cuda_golden(torch):
+    """The example device env against the sequence the unmodified reference produced on a
+    B200 (oracle/gen_golden_env.py gpu): same tolerance as the host env's test, because the
+    reference's numpy.var() may sit an ulp off the exactly rounded variance."""
+
+    from examples import custom_environments
+    from reinfocus_b200.environments import state_initializer
+
+    path = os.path.join(GOLDEN, "gpu_env_vector_discrete_steps.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated yet")
+    gold = numpy.load(path)
+    env = custom_environments.DeviceVectorDiscreteSteps(
+        max_episode_steps=20, num_envs=8,
+        initializer=state_initializer.RangedInitializer([[ENDS]] * 2, generator=_generator(77)))
+    obs0, _ = env.reset()
+    numpy.testing.assert_allclose(obs0.cpu().numpy(), gold["obs0"], rtol=0, atol=2.5e-7)
+    for step, step_actions in enumerate(gold["actions"]):
+        obs, rewards, terminated, truncated, _ = env.step(torch.as_tensor(step_actions, device="cuda"))
+        numpy.testing.assert_array_equal(truncated.cpu().numpy(), gold["trunc"][step])
+        numpy.testing.assert_array_equal(terminated.cpu().numpy(), gold["term"][step])
+        numpy.testing.assert_allclose(obs.cpu().numpy(), gold["obs"][step], rtol=0, atol=2.5e-7)
+        numpy.testing.assert_allclose(rewards.cpu().numpy(), gold["rew"][step], rtol=0, atol=2.5e-7)
+    assert gold["trunc"].any()
+
+
+def test_jump_device_env_equals_host_env(torch):
+    """ContinuousJumps composition (float32 actions, Stopped * OnTarget rewards), no time
+    limit, including jumps below the stop threshold."""
+
+    host, device = _pair(6, seed=32, frame_height=64, spp=10, kind="jumps", max_steps=0)
+    raw = numpy.random.Generator(numpy.random.PCG64(4)).uniform(-1, 1, (50, 6, 1))
+    raw[::4] *= 0.01
+    actions = raw.astype(numpy.float32)
+    assert _assert_same_rollout(host, device, actions) > 0
+
+
+def test_device_env_with_more_envs_than_one_scan_chunk(torch):
+    """2500 envs (three chunks of the ordered restart scan) at a small frame: restarts keep
+    drawing their first states in env order from the one generator."""
+
+    host, device = _pair(2500, seed=33, frame_height=12, spp=3)
+    actions = numpy.random.Generator(numpy.random.PCG64(5)).integers(0, 13, (25, 2500))
+    assert _assert_same_rollout(host, device, actions) > 2500
+
+
+def test_device_env_takes_device_actions_and_rejects_bad_ones(torch):
+    _, device = _pair(4, seed=34, frame_height=32, spp=4)
+    with pytest.raises(AssertionError):
+        device.step(numpy.zeros(4, dtype=numpy.int64))  # before reset
+    device.reset()
+    obs, rewards, terminated, truncated, info = device.step(
+        torch.tensor([0, 6, 12, -1], dtype=torch.int32, device="cuda"))
+    assert obs.shape == (4, 4) and obs.dtype == torch.float32 and bool((obs.abs() <= 1).all())
+    assert rewards.dtype == torch.float64 and truncated.dtype == torch.bool
+    assert not bool(terminated.any()) and info == {}
+    with pytest.raises(AssertionError, match="action"):
+        device.step(numpy.array([0, 1, 13, 2]))
+    with pytest.raises(AssertionError):
+        device.step(numpy.array([0, 1, 2, 3]))  # must be reset after a failed step
+    device.reset()
+    device.step(numpy.array([0, 1, 2, 3]))
+    with pytest.raises(AssertionError):
+        device.step(numpy.array([0, 1, 2]))
+
+
+def test_scene_packing_on_device_equals_host_packing(torch):
+    """rf_set_scene_device against FastWorlds / FastCameras._make_device_data + upload: the
+    default camera through FastRenderer, a tilted one through the context."""
+
+    from reinfocus_b200 import _lib
+    from reinfocus_b200.graphics import camera, render, vector, world
+
+    rng = numpy.random.Generator(numpy.random.PCG64(6))
+    targets = rng.uniform(5, 10, 7).astype(numpy.float32)
+    planes = rng.uniform(5, 10, 7).astype(numpy.float32)
+    host, device = render.FastRenderer(samples_per_pixel=5), render.FastRenderer(samples_per_pixel=5)
+    states = torch.as_tensor(numpy.stack([targets, planes], axis=1), device="cuda")
+    for _ in range(2):
+        want = host.step_focus(targets, planes, 48)
+        got = device.step_focus_device(states[:, 0], states[:, 1], 48)
+        numpy.testing.assert_array_equal(got.cpu().numpy(), want)
+    # host-side use of the same renderer afterwards uploads its own scene again
+    numpy.testing.assert_array_equal(device.step_focus(targets[:3], planes[:3], 48),
+                                     host.step_focus(targets[:3], planes[:3], 48))
+
+    cameras = camera.FastCameras(aspect_ratio=1, look_from=vector.v3f(0.3, -0.2, 0.5),
+                                 look_at=vector.v3f(0.1, 0.4, -9.0), up=vector.v3f(0.1, 1.0, 0.05),
+                                 aperture=0.23, vfov=28)
+    worlds = world.FastWorlds(r_size=17)
+    cameras.update(planes)
+    worlds.update(targets)
+    a, b = _lib.Context(), _lib.Context()
+    a.set_world(worlds.device_data())
+    a.set_cameras(cameras.device_data(), *cameras.statics)
+    b.set_scene_device(7, states[:, 0].data_ptr(), states[:, 1].data_ptr(), 2,
+                       _lib.ScenePacking(worlds.packing_constant, *cameras.packing_constants))
+    frames = [torch.empty((7, 40, 40, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    a.render(7, 40, 40, 6, frames[0].data_ptr(), None)
+    b.render(7, 40, 40, 6, frames[1].data_ptr(), None)
+    assert a.last_trace_kernel() == 0 and b.last_trace_kernel() == 0
+    assert int(frames[0].max()) > 0
+    assert torch.equal(frames[0], frames[1])
