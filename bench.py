@@ -272,6 +272,30 @@ def run_ours(args):
     env_loop_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     del env
 
+    # the same env with the whole step on the device (rf_env_step): actions are device
+    # tensors (a policy on the GPU), observations / rewards stay there; one sync at the end
+    env = custom_environments.DeviceVectorDiscreteSteps(
+        max_episode_steps=20, num_envs=n_local,
+        initializer=state_initializer.RangedInitializer([[custom_environments.ENDS]] * 2, seed=1234 + rank))
+    action_rng = numpy.random.Generator(numpy.random.PCG64DXSM(4321 + rank))
+    device_actions = torch.from_numpy(
+        action_rng.integers(0, 13, (args.warmup + args.steps, n_local))).to(device)
+    env.reset()
+    device_resets = 0
+    for i in range(args.warmup):
+        env.step(device_actions[i])
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        env.step(device_actions[args.warmup + i])
+        device_resets += env.last_resets
+    torch.cuda.synchronize()
+    barrier()
+    device_env_loop_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    env.close()
+    del env
+
     if rank != 0:
         return
 
@@ -345,6 +369,14 @@ def run_ours(args):
                     "focus + rewards + enders + same-step re-render of reset envs, host API",
             "value": args.envs / (env_loop_ms * 1e-3), "unit": UNIT, "ms_per_step": env_loop_ms,
             "resets_per_step_rank0": resets / args.steps,
+        },
+        "env_loop_device": {
+            "what": "DeviceVectorDiscreteSteps.step (rf_env_step): the same env with transformer, "
+                    "enders, observers, rewarders and auto-reset on the GPU, device actions in, "
+                    "device observations / rewards out",
+            "value": args.envs / (device_env_loop_ms * 1e-3), "unit": UNIT,
+            "ms_per_step": device_env_loop_ms,
+            "resets_per_step_rank0": device_resets / args.steps,
         },
         "rng_init_s": rng_init_s,
         "device": {"sm_count": info["sm_count"], "cc": list(info["cc"])},

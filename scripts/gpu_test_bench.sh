@@ -7,5 +7,5 @@ timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 
 tail -6 gpurun_out/${TAG}_pytest.log; tail -2 gpurun_out/${TAG}_smoke.log; tail -2 gpurun_out/${TAG}_bench.err; python - <<PY
 import json
 d=json.load(open("gpurun_out/${TAG}_bench.json"))
-print({k:d[k] for k in ("value","ms_per_step","rays_per_s")}, d["e2e"], d["roofline"]["launch_ms"], d["roofline_focus"]["launch_ms"], d["clocks"])
+print({k:d[k] for k in ("value","ms_per_step","rays_per_s")}, d["env_loop"], d["env_loop_device"], d["e2e"], d["roofline"]["launch_ms"], d["roofline_focus"]["launch_ms"], d["clocks"])
 PY
