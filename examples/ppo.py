@@ -155,10 +155,96 @@ class RolloutCollector:
         return data
 
 
+class DeviceRunningMeanStd:
+    """RunningMeanStd on the GPU (float64 torch tensors, no host sync)."""
+
+    def __init__(self, shape, device):
+        self.mean = torch.zeros(shape, dtype=torch.float64, device=device)
+        self.var = torch.ones(shape, dtype=torch.float64, device=device)
+        self.count = 1e-4
+
+    def update(self, batch: torch.Tensor):
+        batch = batch.to(torch.float64)
+        batch_mean, batch_var, batch_count = batch.mean(dim=0), batch.var(dim=0, unbiased=False), batch.shape[0]
+        delta = batch_mean - self.mean
+        total = self.count + batch_count
+        self.mean = self.mean + delta * batch_count / total
+        m2 = self.var * self.count + batch_var * batch_count + delta**2 * self.count * batch_count / total
+        self.var = m2 / total
+        self.count = total
+
+
+class DeviceRolloutCollector:
+    """RolloutCollector for a DeviceVectorEnvironment: observations, rewards, the frame stack,
+    the running normalisation, the buffer and GAE all stay on the GPU; the policy's actions go
+    to the env as a device tensor. Same arithmetic as RolloutCollector, in torch."""
+
+    def __init__(self, env, policy: ActorCritic, config: PPOConfig, device):
+        self.env, self.policy, self.cfg, self.device = env, policy, config, device
+        self.n = env.num_envs
+        obs_dim = env.single_observation_space.shape[0]
+        self.stack = torch.zeros((self.n, config.frame_stack, obs_dim), dtype=torch.float32, device=device)
+        self.obs_rms = DeviceRunningMeanStd((config.frame_stack * obs_dim,), device)
+        self.ret_rms = DeviceRunningMeanStd((), device)
+        self.returns = torch.zeros(self.n, dtype=torch.float64, device=device)
+        obs, _ = env.reset()
+        self.stack[:, -1] = obs
+        self.env_steps = 0
+
+    def _normalised(self, update: bool):
+        flat = self.stack.reshape(self.n, -1)
+        if not self.cfg.normalize:
+            return flat
+        if update:
+            self.obs_rms.update(flat)
+        return torch.clamp((flat - self.obs_rms.mean) / torch.sqrt(self.obs_rms.var + 1e-8), -10, 10).to(
+            torch.float32)
+
+    def collect(self):
+        cfg, n, T = self.cfg, self.n, self.cfg.n_steps
+        buf = {k: [] for k in ("obs", "act", "logp", "val", "rew", "done")}
+        obs = self._normalised(update=True)
+        for _ in range(T):
+            with torch.no_grad():
+                dist, value = self.policy(obs)
+                action = dist.sample()
+                logp = dist.log_prob(action)
+            next_obs, reward, terminated, truncated, _ = self.env.step(action)
+            done = terminated | truncated
+            self.env_steps += n
+            self.returns = self.returns * cfg.gamma + reward
+            if cfg.normalize:
+                self.ret_rms.update(self.returns)
+                reward = torch.clamp(reward / torch.sqrt(self.ret_rms.var + 1e-8), -10, 10)
+            self.returns = torch.where(done, torch.zeros_like(self.returns), self.returns)
+            for key, value_ in (("obs", obs), ("act", action), ("logp", logp), ("val", value),
+                                ("rew", reward.to(torch.float32)), ("done", done)):
+                buf[key].append(value_)
+            self.stack[:, :-1] = self.stack[:, 1:].clone()
+            self.stack[:, :-1] *= (~done).to(torch.float32)[:, None, None]
+            self.stack[:, -1] = next_obs
+            obs = self._normalised(update=True)
+        with torch.no_grad():
+            _, last_value = self.policy(obs)
+        data = {k: torch.stack(v) for k, v in buf.items()}
+        adv = torch.zeros((T, n), dtype=torch.float32, device=self.device)
+        last = torch.zeros(n, dtype=torch.float32, device=self.device)
+        next_value = last_value
+        for t in reversed(range(T)):
+            not_done = 1.0 - data["done"][t].to(torch.float32)
+            delta = data["rew"][t] + cfg.gamma * next_value * not_done - data["val"][t]
+            last = delta + cfg.gamma * cfg.gae_lambda * not_done * last
+            adv[t] = last
+            next_value = data["val"][t]
+        data["adv"] = adv
+        data["ret"] = adv + data["val"]
+        return data
+
+
 def ppo_update(policy: ActorCritic, optimizer, data, cfg: PPOConfig, device, max_minibatches=None):
     """Clipped-surrogate PPO epochs over one rollout; returns the last losses."""
 
-    flat = {k: torch.from_numpy(v.reshape((-1,) + v.shape[2:])).to(device) for k, v in data.items()
+    flat = {k: torch.as_tensor(v).reshape((-1,) + tuple(v.shape[2:])).to(device) for k, v in data.items()
             if k in ("obs", "act", "logp", "adv", "ret")}
     size = flat["obs"].shape[0]
     distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
@@ -183,7 +269,7 @@ def ppo_update(policy: ActorCritic, optimizer, data, cfg: PPOConfig, device, max
                     param.grad /= torch.distributed.get_world_size()
             nn.utils.clip_grad_norm_(policy.parameters(), cfg.max_grad_norm)
             optimizer.step()
-            stats = {"loss": float(loss), "pg": float(pg_loss), "vf": float(vf_loss), "entropy": float(entropy)}
+            stats = {name: float(term.detach()) for name, term in (("loss", loss), ("pg", pg_loss), ("vf", vf_loss), ("entropy", entropy))}
             batches += 1
             if max_minibatches and batches >= max_minibatches:
                 return stats
@@ -191,9 +277,11 @@ def ppo_update(policy: ActorCritic, optimizer, data, cfg: PPOConfig, device, max
 
 
 def train(num_envs: int = 8, rollouts: int = 2, config: PPOConfig | None = None, seed: int = 0,
-          max_minibatches: int | None = None, log=print):
+          max_minibatches: int | None = None, log=print, device_env: bool = False):
     """Collects ``rollouts`` rollouts of n_steps on VectorDiscreteSteps(num_envs) (per rank)
-    and runs the PPO update after each. Returns per-rollout statistics."""
+    and runs the PPO update after each. Returns per-rollout statistics. ``device_env`` steps
+    DeviceVectorDiscreteSteps instead: the same env sequences, with the env step, the buffer
+    and the normalisation on the GPU."""
 
     from examples import custom_environments
     from reinfocus_b200 import parallel
@@ -205,13 +293,17 @@ def train(num_envs: int = 8, rollouts: int = 2, config: PPOConfig | None = None,
     device = torch.device("cuda", local_rank)
     torch.manual_seed(seed)  # same policy weights on every rank
     first, last = parallel.shard_bounds(num_envs, world, rank)
-    env = custom_environments.VectorDiscreteSteps(
-        max_episode_steps=20, num_envs=last - first,
-        initializer=state_initializer.RangedInitializer([[custom_environments.ENDS]] * 2, seed=seed + rank))
+    initializer = state_initializer.RangedInitializer([[custom_environments.ENDS]] * 2, seed=seed + rank)
+    if device_env:
+        env = custom_environments.DeviceVectorDiscreteSteps(
+            max_episode_steps=20, num_envs=last - first, initializer=initializer)
+    else:
+        env = custom_environments.VectorDiscreteSteps(
+            max_episode_steps=20, num_envs=last - first, initializer=initializer)
     obs_dim = env.single_observation_space.shape[0] * cfg.frame_stack
     policy = ActorCritic(obs_dim, env.single_action_space.n, cfg.net_arch).to(device)
     optimizer = torch.optim.Adam(policy.parameters(), lr=cfg.learning_rate, eps=1e-5)
-    collector = RolloutCollector(env, policy, cfg, device)
+    collector = (DeviceRolloutCollector if device_env else RolloutCollector)(env, policy, cfg, device)
     torch.manual_seed(seed + 1000 + rank)  # different action samples per rank
     history = []
     for i in range(rollouts):
@@ -221,14 +313,14 @@ def train(num_envs: int = 8, rollouts: int = 2, config: PPOConfig | None = None,
         t_collect = time.perf_counter() - t0
         if world > 1:
             # the policy rank sees every env's observations (north star: NCCL obs gather)
-            parallel.gather_observations(torch.from_numpy(data["obs"][-1]).to(device), num_envs)
+            parallel.gather_observations(torch.as_tensor(data["obs"][-1]).to(device), num_envs)
         t1 = time.perf_counter()
         stats = ppo_update(policy, optimizer, data, cfg, device, max_minibatches)
         torch.cuda.synchronize()
         entry = {"rollout": i, "env_steps": (last - first) * cfg.n_steps,
                  "collect_s": t_collect, "update_s": time.perf_counter() - t1,
                  "env_steps_per_s": (last - first) * cfg.n_steps / t_collect * world,
-                 "mean_reward": float(data["rew"].mean()), **stats}
+                 "mean_reward": float(data["rew"].mean()), "device_env": device_env, **stats}
         history.append(entry)
         if rank == 0:
             log(entry)

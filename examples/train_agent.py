@@ -20,6 +20,8 @@ def main():
     parser.add_argument("--num-envs", type=int, default=None, help="default: n_envs of the yml")
     parser.add_argument("--rollouts", type=int, default=2)
     parser.add_argument("--max-minibatches", type=int, default=None)
+    parser.add_argument("--device-env", action="store_true",
+                        help="step DeviceVectorDiscreteSteps: env step, buffer and normalisation on the GPU")
     args = parser.parse_args()
 
     import yaml
@@ -31,7 +33,8 @@ def main():
     with open(conf) as f:
         n_envs = args.num_envs or yaml.safe_load(f)[args.env]["n_envs"]
     history = ppo.train(num_envs=n_envs, rollouts=args.rollouts, config=cfg,
-                        max_minibatches=args.max_minibatches, log=lambda e: print(json.dumps(e)))
+                        max_minibatches=args.max_minibatches, log=lambda e: print(json.dumps(e)),
+                        device_env=args.device_env)
     return history
 
 

@@ -207,3 +207,37 @@ def test_scene_packing_on_device_equals_host_packing(torch):
     assert a.last_trace_kernel() == 0 and b.last_trace_kernel() == 0
     assert int(frames[0].max()) > 0
     assert torch.equal(frames[0], frames[1])
+
+
+def test_ppo_rollout_on_the_device_env_equals_the_host_rollout(torch):
+    """examples/ppo.py with device_env=True: the rollout buffer (observations after frame
+    stacking and running normalisation, actions, rewards, dones, advantages) equals the one
+    collected through the host env with the same seeds, up to float64 summation order in the
+    running moments."""
+
+    from examples import custom_environments, ppo
+    from reinfocus_b200.environments import state_initializer
+
+    cfg = ppo.PPOConfig(n_steps=24)
+    device = torch.device("cuda", torch.cuda.current_device())
+    data = {}
+    for name, env_cls, collector_cls in (
+            ("host", custom_environments.VectorDiscreteSteps, ppo.RolloutCollector),
+            ("device", custom_environments.DeviceVectorDiscreteSteps, ppo.DeviceRolloutCollector)):
+        env = env_cls(max_episode_steps=20, num_envs=6,
+                      initializer=state_initializer.RangedInitializer([[ENDS]] * 2, seed=9))
+        torch.manual_seed(0)
+        policy = ppo.ActorCritic(4 * cfg.frame_stack, 13, cfg.net_arch).to(device)
+        collector = collector_cls(env, policy, cfg, device)
+        torch.manual_seed(1)
+        data[name] = {k: torch.as_tensor(v).cpu().numpy() for k, v in collector.collect().items()}
+    assert data["host"]["done"].any()
+    numpy.testing.assert_array_equal(data["device"]["act"], data["host"]["act"])
+    numpy.testing.assert_array_equal(data["device"]["done"], data["host"]["done"])
+    for key in ("obs", "rew", "val", "logp", "adv", "ret"):
+        assert data["device"][key].shape == data["host"][key].shape
+        numpy.testing.assert_allclose(data["device"][key], data["host"][key], rtol=1e-4, atol=1e-4,
+                                      err_msg=key)
+    history = ppo.train(num_envs=6, rollouts=1, config=cfg, max_minibatches=2, log=lambda e: None,
+                        device_env=True)
+    assert history[0]["device_env"] and numpy.isfinite(history[0]["loss"])
