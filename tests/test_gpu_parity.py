@@ -356,6 +356,65 @@ def test_batch_split_property_at_64_envs(torch):
         numpy.testing.assert_array_equal(single.render(height)[0], frames[e])
 
 
+def test_full_benchmark_batch_matches_oracle_on_sampled_envs(torch):
+    """BASELINE config at full size - 4096 envs x 300x300 x 100 spp, one step - checked where
+    the oracle can follow in seconds: for sampled envs (first, last, a restart-sized prefix
+    boundary, random ones) the focus value and the RNG states left behind equal the oracle's
+    step of that env alone, started from that env's slice of the initial states."""
+
+    n, height, spp = 4096, 300, 100
+    pixels = height * height
+    rng = numpy.random.Generator(numpy.random.PCG64DXSM(1234))
+    targets = rng.uniform(5, 10, n).astype(numpy.float32)
+    planes = rng.uniform(5, 10, n).astype(numpy.float32)
+    renderer = _renderer(samples_per_pixel=spp)
+    ctx = renderer.context
+    ctx.rng_ensure(n * pixels)
+    sampled = [0, 1, 512, 513, 2047, 3333, 4095]
+    before = {e: ctx.rng_export(e * pixels, pixels) for e in sampled}
+    focus = renderer.step_focus(targets, planes, height)
+    assert ctx.last_trace_kernel() == 4 and ctx.last_focus_kernel() == 1
+    assert focus.shape == (n,) and numpy.isfinite(focus).all()
+    world, cam = oracle.pack_world(targets), oracle.pack_cameras(planes)
+    for e in sampled:
+        states = before[e].copy()
+        want = oracle.step(world[e:e + 1], cam[e:e + 1], height, spp, states)
+        assert focus[e] == want[0], (e, focus[e], want[0])
+        numpy.testing.assert_array_equal(ctx.rng_export(e * pixels, pixels), states)
+    del renderer
+
+
+def test_pixel_index_beyond_2_31(torch):
+    """24 000 envs x 300x300 = 2.16e9 pixels (34.6 GB of RNG states): the pixel index is
+    64-bit as in the reference (render.py:217). Envs on both sides of the 2^31 boundary, and
+    the last one, against the oracle from their own slices of the initial states."""
+
+    n, height, spp = 24000, 300, 1
+    pixels = height * height
+    assert n * pixels > 2**31
+    rng = numpy.random.Generator(numpy.random.PCG64DXSM(99))
+    targets = rng.uniform(5, 10, n).astype(numpy.float32)
+    planes = rng.uniform(5, 10, n).astype(numpy.float32)
+    renderer = _renderer(samples_per_pixel=spp)
+    ctx = renderer.context
+    ctx.rng_ensure(n * pixels)
+    boundary = 2**31 // pixels  # the env whose pixels straddle index 2^31
+    sampled = [0, boundary - 1, boundary, boundary + 1, n - 1]
+    before = {e: ctx.rng_export(e * pixels, pixels) for e in sampled}
+    # the state at index 2^31 + 5 is what the jump chain says it is
+    reference_states = oracle.rng_states(4096, 0)
+    numpy.testing.assert_array_equal(ctx.rng_export(0, 4096), reference_states)
+    focus = renderer.step_focus(targets, planes, height)
+    world, cam = oracle.pack_world(targets), oracle.pack_cameras(planes)
+    for e in sampled:
+        states = before[e].copy()
+        want = oracle.step(world[e:e + 1], cam[e:e + 1], height, spp, states)
+        assert focus[e] == want[0], (e, focus[e], want[0])
+        numpy.testing.assert_array_equal(ctx.rng_export(e * pixels, pixels), states)
+    del renderer
+    torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------- focus measure (a12)
 
 
