@@ -355,6 +355,11 @@ def run_ours(args):
                            f"theoretical 148 SM x 128 x 2 x 1.965 GHz = {THEORETICAL_FP32_TFLOPS:.1f}",
             "algorithmic_flop_per_ray": FLOP_PER_RAY, "rays_per_launch": rays_local,
             "launch_ms": trace_ms, "rays_per_s": rays_local / (trace_ms * 1e-3),
+            # what actually binds this kernel: warp instructions issued per second
+            # against 4 schedulers x 1 instruction / clock / SM; instruction count from ncu
+            "issue": issue_view(traffic, n_local, trace_ms, info["sm_count"], clocks.summary()),
+            "hbm": {"achieved": n_local * HEIGHT * HEIGHT * 33 / (trace_ms * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s"},
         },
         "roofline_focus": {
             "kernel": "rf::focus_kernel", "bound": "hbm", "achieved": focus_bytes / (focus_ms * 1e-3) / 1e9,
@@ -391,6 +396,20 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world_size > 1:
         dist.destroy_process_group()
+
+
+def issue_view(traffic, n_local, trace_ms, sm_count, clock_summary):
+    per_env = traffic.get("trace_kernel_warp_inst_per_env")
+    mhz = clock_summary.get("sm_mhz") or clock_summary.get("sm_max_mhz")
+    if not per_env or not mhz:
+        return None
+    achieved = per_env * n_local / (trace_ms * 1e-3) / 1e9
+    peak = sm_count * 4 * mhz * 1e6 / 1e9
+    return {"warp_inst_per_launch": per_env * n_local, "achieved": achieved, "peak": peak,
+            "unit": "G warp-inst/s", "frac": achieved / peak,
+            "source": "smsp__inst_executed.sum per env from ncu at 256 envs (profiles/ncu_traffic.json); "
+                      "peak = SMs x 4 schedulers x sampled SM clock",
+            "ncu_pct": traffic.get("trace_kernel_ncu_pct")}
 
 
 def main():

@@ -242,9 +242,17 @@ int rf_env_reset(rf_env *env, float *d_obs, void *stream);
  * which is known before the main render starts; the outputs are stream-ordered. */
 int rf_env_step(rf_env *env, const void *d_actions, int action_kind, float *d_obs,
                 double *d_rewards, uint8_t *d_truncated, int *h_resets, void *stream);
-/* Synchronous copies of the env's state (parity tests, checkpoints): any pointer may be
- * NULL. h_states float32 [n, 2], h_steps / h_diverging int32 [n]. */
-int rf_env_export(rf_env *env, float *h_states, int *h_steps, int *h_diverging);
+/* Synchronous copies of the env's episode state to / from host memory (parity tests,
+ * checkpoint / resume; the reference cannot serialise an env). Together with the generator
+ * (rf_env_get/set_generator) and the renderer's RNG states (rf_rng_export/import) this is
+ * everything a resumed run needs to continue bit-identically. h_states float32 [n, 2],
+ * h_steps / h_diverging int32 [n], h_last_gap float32 [n] (DivergingEnder), h_old_obs
+ * float32 [n, 2] (DeltaObserver), h_old_plane float32 [n] (Delta / Stopped rewarder). Export
+ * skips NULL pointers; import needs all of them and stands in for a reset. */
+int rf_env_export(rf_env *env, float *h_states, int *h_steps, int *h_diverging, float *h_last_gap,
+                  float *h_old_obs, float *h_old_plane);
+int rf_env_import(rf_env *env, const float *h_states, const int *h_steps, const int *h_diverging,
+                  const float *h_last_gap, const float *h_old_obs, const float *h_old_plane);
 
 /* -------------------------------------------------------------------------------------
  * Self-checks and measurement helpers (used by tests/ and bench.py).

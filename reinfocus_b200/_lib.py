@@ -19,7 +19,7 @@ RF_ERR_CUDA = -2
 RF_ERR_NOMEM = -3
 RF_ERR_NO_SCENE = -4
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH, SELFTEST_CONST_DIV = 0, 1, 2, 3
 OPT_FORCE_GENERIC = 0
@@ -118,7 +118,8 @@ _SIGNATURES = {
     "rf_env_reset": (ctypes.c_int, [_vp, _vp, _vp]),
     "rf_env_step": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp, _vp,
                                    ctypes.POINTER(ctypes.c_int), _vp]),
-    "rf_env_export": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "rf_env_export": (ctypes.c_int, [_vp] + [_vp] * 6),
+    "rf_env_import": (ctypes.c_int, [_vp] + [_vp] * 6),
     "rf_selftest": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int,
                                    ctypes.POINTER(ctypes.c_int64), _vp]),
     "rf_set_option": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
@@ -414,13 +415,28 @@ class DeviceEnv:
                                           _stream_ptr(stream, self._context.device)))
         return resets.value
 
+    _EXPORT_LAYOUT = (("states", numpy.float32, 2), ("steps", numpy.int32, 1),
+                      ("diverging", numpy.int32, 1), ("last_gap", numpy.float32, 1),
+                      ("old_obs", numpy.float32, 2), ("old_plane", numpy.float32, 1))
+
     def export(self) -> dict:
-        states = numpy.empty((self.num_envs, 2), dtype=numpy.float32)
-        steps = numpy.empty(self.num_envs, dtype=numpy.int32)
-        diverging = numpy.empty(self.num_envs, dtype=numpy.int32)
-        self._check(self._lib.rf_env_export(self._handle, states.ctypes.data, steps.ctypes.data,
-                                            diverging.ctypes.data))
-        return {"states": states, "steps": steps, "diverging": diverging}
+        """Host copies of the per-env episode state."""
+
+        arrays = {name: numpy.empty((self.num_envs, width) if width > 1 else self.num_envs, dtype=dtype)
+                  for name, dtype, width in self._EXPORT_LAYOUT}
+        self._check(self._lib.rf_env_export(
+            self._handle, *[arrays[name].ctypes.data for name, _, _ in self._EXPORT_LAYOUT]))
+        return arrays
+
+    def load(self, arrays: dict):
+        """Restores what ``export`` returned (stands in for a reset)."""
+
+        ordered = []
+        for name, dtype, width in self._EXPORT_LAYOUT:
+            array = numpy.ascontiguousarray(arrays[name], dtype=dtype)
+            assert array.shape == ((self.num_envs, width) if width > 1 else (self.num_envs,)), name
+            ordered.append(array)
+        self._check(self._lib.rf_env_import(self._handle, *[array.ctypes.data for array in ordered]))
 
 
 _shared_contexts: dict[int, Context] = {}

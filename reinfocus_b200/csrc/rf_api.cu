@@ -18,7 +18,7 @@
 #include "rf_rng.cuh"
 #include "rf_tracer.cuh"
 
-#define RF_ABI_VERSION 3
+#define RF_ABI_VERSION 4
 
 namespace {
 
@@ -932,17 +932,53 @@ int rf_env_step(rf_env *env, const void *d_actions, int action_kind, float *d_ob
                        (cudaStream_t)stream);
 }
 
-int rf_env_export(rf_env *env, float *h_states, int *h_steps, int *h_diverging) {
-    if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_export: env is NULL");
+namespace {
+
+// host <-> device copies of the per-env arrays (to_host or from host)
+int env_copy_arrays(rf_env *env, bool to_host, float *h_states, int *h_steps, int *h_diverging,
+                    float *h_last_gap, float *h_old_obs, float *h_old_plane) {
     rf_ctx *ctx = env->ctx;
     DeviceGuard guard(ctx->device);
     const size_t n = (size_t)env->params.n;
+    const rf::EnvArrays &a = env->arrays;
     RF_CUDA(ctx, cudaDeviceSynchronize());
-    if (h_states)
-        RF_CUDA(ctx, cudaMemcpy(h_states, env->arrays.states, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost));
-    if (h_steps) RF_CUDA(ctx, cudaMemcpy(h_steps, env->arrays.steps, sizeof(int) * n, cudaMemcpyDeviceToHost));
-    if (h_diverging)
-        RF_CUDA(ctx, cudaMemcpy(h_diverging, env->arrays.diverging, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    struct Item {
+        void *host;
+        void *device;
+        size_t bytes;
+    } items[] = {
+        {h_states, a.states, sizeof(float) * 2 * n},     {h_steps, a.steps, sizeof(int) * n},
+        {h_diverging, a.diverging, sizeof(int) * n},     {h_last_gap, a.last_gap, sizeof(float) * n},
+        {h_old_obs, a.old_obs, sizeof(float) * 2 * n},   {h_old_plane, a.old_plane, sizeof(float) * n},
+    };
+    for (const Item &item : items) {
+        if (!item.host) continue;
+        if (to_host)
+            RF_CUDA(ctx, cudaMemcpy(item.host, item.device, item.bytes, cudaMemcpyDeviceToHost));
+        else
+            RF_CUDA(ctx, cudaMemcpy(item.device, item.host, item.bytes, cudaMemcpyHostToDevice));
+    }
+    return RF_OK;
+}
+
+}  // namespace
+
+int rf_env_export(rf_env *env, float *h_states, int *h_steps, int *h_diverging, float *h_last_gap,
+                  float *h_old_obs, float *h_old_plane) {
+    if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_export: env is NULL");
+    return env_copy_arrays(env, true, h_states, h_steps, h_diverging, h_last_gap, h_old_obs, h_old_plane);
+}
+
+int rf_env_import(rf_env *env, const float *h_states, const int *h_steps, const int *h_diverging,
+                  const float *h_last_gap, const float *h_old_obs, const float *h_old_plane) {
+    if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_import: env is NULL");
+    RF_REQUIRE(env->ctx, h_states && h_steps && h_diverging && h_last_gap && h_old_obs && h_old_plane,
+               "rf_env_import: every array is required");
+    if (int rc = env_copy_arrays(env, false, const_cast<float *>(h_states), const_cast<int *>(h_steps),
+                                 const_cast<int *>(h_diverging), const_cast<float *>(h_last_gap),
+                                 const_cast<float *>(h_old_obs), const_cast<float *>(h_old_plane)))
+        return rc;
+    env->started = true;  // the imported episode state stands in for a reset
     return RF_OK;
 }
 

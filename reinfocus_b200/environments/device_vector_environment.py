@@ -6,7 +6,7 @@ objects in NumPy on the host and only the render + focus measure on the GPU.
 their arithmetic in two small CUDA kernels around the render (rf_env_step), so states,
 observations and rewards live in device memory and a policy on the GPU can act on them
 without a host round trip. Sequences are bit-identical to ``VectorEnvironment`` driven by the
-same generator (tests/test_gpu_parity.py).
+same generator (tests/test_gpu_device_env.py).
 
 Only the compositions of the example envs are understood (anything else raises
 ``NotImplementedError`` - use ``VectorEnvironment`` for it):
@@ -250,6 +250,24 @@ class DeviceVectorEnvironment(gym_compat.VectorEnv):
         """Host copies of the states and ender counters (tests, checkpoints)."""
 
         return self._env.export()
+
+    def state_dict(self) -> dict:
+        """Everything a resumed run needs to continue bit-identically: the per-env episode
+        state, the initializer's generator and the renderer's RNG states (the reference
+        cannot checkpoint an env: its RNG states live in a numba device array)."""
+
+        state, inc = self._env.get_generator()
+        return {"env": self._env.export(), "generator": (state, inc),
+                "rng_states": self._renderer.context.rng_export()}
+
+    def load_state_dict(self, checkpoint: dict):
+        self._env.load(checkpoint["env"])
+        self._env.set_generator(*checkpoint["generator"])
+        context = self._renderer.context
+        context.rng_ensure(len(checkpoint["rng_states"]))
+        context.rng_import(checkpoint["rng_states"])
+        self._renderer.scene_overwritten()
+        self._started = True
 
     # ---------------------------------------------------------------------------- helpers
     def _device_actions(self, actions):

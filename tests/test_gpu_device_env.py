@@ -241,3 +241,27 @@ def test_ppo_rollout_on_the_device_env_equals_the_host_rollout(torch):
     history = ppo.train(num_envs=6, rollouts=1, config=cfg, max_minibatches=2, log=lambda e: None,
                         device_env=True)
     assert history[0]["device_env"] and numpy.isfinite(history[0]["loss"])
+
+
+def test_device_env_checkpoint_and_resume(torch):
+    """state_dict() after 12 steps, loaded into a brand-new env (new context, new renderer):
+    the next 15 steps are those of the uninterrupted run, bit for bit."""
+
+    _, env = _pair(5, seed=35, frame_height=40, spp=6)
+    actions = numpy.random.Generator(numpy.random.PCG64(8)).integers(0, 13, (27, 5))
+    env.reset()
+    for step_actions in actions[:12]:
+        env.step(step_actions)
+    checkpoint = env.state_dict()
+    want = [[t.cpu().numpy() for t in env.step(step_actions)[:4]] for step_actions in actions[12:]]
+    assert any(w[3].any() for w in want), "the continuation should include restarts"
+
+    _, resumed = _pair(5, seed=999, frame_height=40, spp=6)  # different generator on purpose
+    resumed.load_state_dict(checkpoint)
+    for step_actions, w in zip(actions[12:], want):
+        got = [t.cpu().numpy() for t in resumed.step(step_actions)[:4]]
+        for g, ww in zip(got, w):
+            numpy.testing.assert_array_equal(g, ww)
+    assert resumed.generator_state() == env.generator_state()
+    for key, value in env.export_state().items():
+        numpy.testing.assert_array_equal(resumed.export_state()[key], value, err_msg=key)
