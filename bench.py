@@ -362,7 +362,7 @@ def run_ours(args):
                     "peak": hbm_peak, "unit": "GB/s"},
         },
         "roofline_focus": {
-            "kernel": "rf::focus_kernel", "bound": "hbm", "achieved": focus_bytes / (focus_ms * 1e-3) / 1e9,
+            "kernel": "rf::focus_packed_kernel", "bound": "hbm", "achieved": focus_bytes / (focus_ms * 1e-3) / 1e9,
             "peak": hbm_peak, "unit": "GB/s",
             "frac": focus_bytes / (focus_ms * 1e-3) / 1e9 / hbm_peak,
             "traffic": scaled_traffic("focus_kernel_bytes_per_env"),

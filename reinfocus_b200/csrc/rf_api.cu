@@ -229,28 +229,25 @@ int launch_focus_packed(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, 
     p.channels = channels;
     p.segs = (W + rf::kPackedCols - 1) / rf::kPackedCols;
     // rows per warp tile: 4 halo rows are recomputed per tile, so prefer tall tiles, but
-    // keep at least ~4 warps per SM sub-partition in flight for small batches
-    const int64_t want_tiles = (int64_t)ctx->prop.multiProcessorCount * 32;
-    int band = 32;
-    while (band > 4 && (int64_t)n * p.segs * ((H + band - 1) / band) < want_tiles) band /= 2;
+    // keep ~10 waves of 32 warps per SM so that the last wave's tail stays small
+    const int64_t want_tiles = (int64_t)ctx->prop.multiProcessorCount * 32 * 10;
+    int band = H;
+    while (band > 4 && (int64_t)n * p.segs * ((H + band - 1) / band) < want_tiles) band = (band + 1) / 2;
     p.band = band;
     p.bands = (H + band - 1) / band;
-    const int tiles = p.segs * p.bands;
-    const unsigned blocks_x = (unsigned)((tiles + rf::kPackedWarps - 1) / rf::kPackedWarps);
-    for (int first = 0; first < n; first += 65535) {
-        const int cnt = std::min(65535, n - first);
-        p.img = d_img + (int64_t)first * H * W * channels;
-        p.out = d_out + first;
-        p.accum = ctx->d_accum + 2 * (int64_t)first;
-        p.tickets = ctx->d_tickets + first;
-        p.n = cnt;
-        const dim3 grid(blocks_x, cnt);
-        if (channels == 1)
-            rf::focus_packed_kernel<1><<<grid, rf::kPackedWarps * 32, 0, stream>>>(p);
-        else
-            rf::focus_packed_kernel<3><<<grid, rf::kPackedWarps * 32, 0, stream>>>(p);
-        ctx->launches++;
-    }
+    // warps take tiles in one flat order over all envs, so blocks stay full whatever the
+    // number of tiles per env is
+    const int64_t tiles = (int64_t)n * p.segs * p.bands;
+    const int64_t blocks = (tiles + rf::kPackedWarps - 1) / rf::kPackedWarps;
+    if (blocks > 0x7fffffffLL) return fail(ctx, RF_ERR_INVALID, "focus batch too large");
+    p.img = d_img;
+    p.out = d_out;
+    p.n = n;
+    if (channels == 1)
+        rf::focus_packed_kernel<1><<<(unsigned)blocks, rf::kPackedWarps * 32, 0, stream>>>(p);
+    else
+        rf::focus_packed_kernel<3><<<(unsigned)blocks, rf::kPackedWarps * 32, 0, stream>>>(p);
+    ctx->launches++;
     RF_CUDA(ctx, cudaGetLastError());
     return RF_OK;
 }

@@ -16,6 +16,8 @@
 // whole measure is a single launch.
 #pragma once
 
+#include <type_traits>
+
 #include <cstdint>
 
 namespace rf {
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kFocusThreads) focus_kernel(const FocusParams 
 // u16x2 lanes with the native 3-input min/max (VIMNMX3.U16x2):
 //   column pass   lo/mid/hi of each vertical triple (mid = sum - lo - hi)
 //   row pass      median9 = med3(max3(lo's), med3(mid's), min3(hi's))
-//   Laplacian     N+S+E+W+1020-4C >= 0 per lane, clamp to [1020, 1275], subtract 1020
+//   Laplacian     N+S+E+W+1024-4C >= 0 per lane, clamp to [1024, 1279]: low byte = result
 //   sums          IDP.4A on the four packed 8-bit Laplacians
 // Horizontal neighbours come from the adjacent lanes by shuffle, vertical ones from the two
 // previous rows kept in registers. Borders: replicated gray (median), reflect-101 medians
@@ -257,10 +259,11 @@ __device__ __forceinline__ uint32_t load_gray_word(const uint8_t *row, int x, in
 template <int kChannels>
 __global__ void __launch_bounds__(kPackedWarps * 32) focus_packed_kernel(const PackedFocusParams p) {
     const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * kPackedWarps + (threadIdx.x >> 5);
+    const int64_t flat = (int64_t)blockIdx.x * kPackedWarps + (threadIdx.x >> 5);
     const int tiles_per_env = p.segs * p.bands;
-    const int e = blockIdx.y;
-    if (tile >= tiles_per_env) return;  // whole warp
+    const int e = (int)(flat / tiles_per_env);
+    if (e >= p.n) return;  // whole warp
+    const int tile = (int)(flat - (int64_t)e * tiles_per_env);
     const int seg = tile % p.segs, band = tile / p.segs;
     const int H = p.H, W = p.W;
     const int y0 = band * p.band, y1 = min(y0 + p.band, H);
@@ -272,38 +275,64 @@ __global__ void __launch_bounds__(kPackedWarps * 32) focus_packed_kernel(const P
     const uint8_t *img = p.img + (size_t)e * H * W * kChannels;
     const size_t pitch = (size_t)W * kChannels;
 
-    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;  // packs of row r-2
-    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0;  // packs of row r-1
+    uint32_t a1 = 0, a2 = 0, a3 = 0, a4 = 0;  // packs of row r-2
+    uint32_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;  // packs of row r-1
     uint32_t m2a = 0, m2b = 0, m1a = 0, m1b = 0;      // medians of rows r-3 and r-2
     uint32_t sum = 0, sum2 = 0;
-    const uint32_t bias = 1020u | (1020u << 16), top = 1275u | (1275u << 16);
+    // the Laplacian is kept non-negative per 16-bit lane by a bias of 1024, whose low byte is
+    // zero: after clamping to [1024, 1279] the low bytes are the saturated Laplacians
+    const uint32_t bias = 1024u | (1024u << 16), top = 1279u | (1279u << 16);
+    const uint32_t count_mask = counts ? 0xffffffffu : 0u;
+    // (m-1, m0) and (m3, m4) for the Laplacian's left / right neighbours; at the image edges
+    // reflect-101 makes m-1 := m1 and m4 := m2, which is just another byte selection
+    const uint32_t select_left = at_left ? 0x5476u : 0x5432u;
+    const uint32_t select_right = at_right ? 0x1032u : 0x5432u;
 
-    // the next row's gray word is requested one iteration ahead so that its latency hides
-    // behind the current row's arithmetic
-    uint32_t g_next = load_gray_word<kChannels>(img + min(max(y0 - 2, 0), H - 1) * pitch, x0, W);
-    for (int r = y0 - 2; r <= y1 + 1; ++r) {
+    // gray input: one aligned word per lane and row. Lanes left / right of the image load the
+    // first / last word of the row and replicate its outer byte (the border rule) with a
+    // per-lane byte-permute selector, so the row loop has no column cases. The row pointer
+    // walks down with the loop and stops at the image's first / last row (replicated rows).
+    const uint8_t *column = img + (x0 < 0 ? 0 : (x0 >= W ? W - 4 : x0));
+    const uint32_t replicate = x0 < 0 ? 0x0000u : (x0 >= W ? 0x3333u : 0x3210u);
+    const uint8_t *row_ptr = column + (size_t)min(max(y0 - 2, 0), H - 1) * pitch;
+    auto load_row = [&](int row) -> uint32_t {
+        if (kChannels == 1) return __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(row_ptr)), 0u, replicate);
+        return load_gray_word<kChannels>(img + (size_t)min(max(row, 0), H - 1) * pitch, x0, W);
+    };
+    auto next_row = [&](int row) {  // row_ptr: row -> row + 1, clamped to the image
+        if (row >= 0 && row < H - 1) row_ptr += pitch;
+    };
+
+    // one image row r enters: pack it; with kMedian the medians of row r-1 follow, with
+    // kLaplacian the Laplacians of row r-2. The next row's word is requested before the
+    // arithmetic so that its latency hides behind it.
+    uint32_t g_next = load_row(y0 - 2);
+    auto step = [&](int r, auto median_tag, auto laplacian_tag) {
+        constexpr bool kMedian = decltype(median_tag)::value, kLaplacian = decltype(laplacian_tag)::value;
         const uint32_t g = g_next;
-        if (r <= y1) g_next = load_gray_word<kChannels>(img + min(max(r + 1, 0), H - 1) * pitch, x0, W);
-        const uint32_t gl = __shfl_up_sync(0xffffffffu, g, 1);
+        next_row(r);
+        if (r <= y1) g_next = load_row(r + 1);
         const uint32_t gr = __shfl_down_sync(0xffffffffu, g, 1);
-        // zero-extended column pairs (x0-1,x0) (x0,x0+1) (x0+1,x0+2) (x0+2,x0+3) (x0+3,x0+4)
-        const uint32_t lz = gl >> 24, rz = gr & 255u;
-        const uint32_t c0 = __byte_perm(lz, g, 0x2410);
+        // zero-extended column pairs (x0,x0+1) (x0+1,x0+2) (x0+2,x0+3) (x0+3,x0+4); the pair
+        // (x0-1,x0) is the left lane's fourth pair, so its sorted triple comes by shuffle
+        const uint32_t rz = gr & 255u;
         const uint32_t c1 = __byte_perm(g, 0u, 0x4140);
         const uint32_t c2 = __byte_perm(g, 0u, 0x4241);
         const uint32_t c3 = __byte_perm(g, 0u, 0x4342);
         const uint32_t c4 = __byte_perm(rz, g, 0x2017);
-        if (r >= y0) {
+        if (kMedian) {
             // column pass on rows r-2, r-1, r
-            const uint32_t lo0 = min3x2(a0, b0, c0), hi0 = max3x2(a0, b0, c0), md0 = a0 + b0 + c0 - lo0 - hi0;
             const uint32_t lo1 = min3x2(a1, b1, c1), hi1 = max3x2(a1, b1, c1), md1 = a1 + b1 + c1 - lo1 - hi1;
             const uint32_t lo2 = min3x2(a2, b2, c2), hi2 = max3x2(a2, b2, c2), md2 = a2 + b2 + c2 - lo2 - hi2;
             const uint32_t lo3 = min3x2(a3, b3, c3), hi3 = max3x2(a3, b3, c3), md3 = a3 + b3 + c3 - lo3 - hi3;
             const uint32_t lo4 = min3x2(a4, b4, c4), hi4 = max3x2(a4, b4, c4), md4 = a4 + b4 + c4 - lo4 - hi4;
+            const uint32_t lo0 = __shfl_up_sync(0xffffffffu, lo4, 1);
+            const uint32_t md0 = __shfl_up_sync(0xffffffffu, md4, 1);
+            const uint32_t hi0 = __shfl_up_sync(0xffffffffu, hi4, 1);
             // row pass: medians of row r-1 for pixels (x0, x0+1) and (x0+2, x0+3)
             const uint32_t ma = med3x2(max3x2(lo0, lo1, lo2), med3x2(md0, md1, md2), min3x2(hi0, hi1, hi2));
             const uint32_t mb = med3x2(max3x2(lo2, lo3, lo4), med3x2(md2, md3, md4), min3x2(hi2, hi3, hi4));
-            if (r >= y0 + 2) {
+            if (kLaplacian) {
                 // Laplacian of row y = r-2: centre m1, up m2 (row r-3), down m (row r-1);
                 // reflect-101 at the top / bottom image rows
                 const int y = r - 2;
@@ -312,26 +341,34 @@ __global__ void __launch_bounds__(kPackedWarps * 32) focus_packed_kernel(const P
                 const uint32_t nl = __shfl_up_sync(0xffffffffu, m1b, 1);
                 const uint32_t nr = __shfl_down_sync(0xffffffffu, m1a, 1);
                 const uint32_t mid = __byte_perm(m1a, m1b, 0x5432);  // (m1, m2)
-                // (m-1, m0) and (m3, m4); at the image edges m-1 := m1 and m4 := m2
-                const uint32_t la = at_left ? __byte_perm(m1a, m1a, 0x1032) : __byte_perm(nl, m1a, 0x5432);
-                const uint32_t rb = at_right ? __byte_perm(m1b, m1b, 0x1032) : __byte_perm(m1b, nr, 0x5432);
+                const uint32_t la = __byte_perm(nl, m1a, select_left);
+                const uint32_t rb = __byte_perm(m1b, nr, select_right);
                 uint32_t va = ua + da + la;
                 va = va + mid + bias - 4u * m1a;
                 uint32_t vb = ub + db + mid;
                 vb = vb + rb + bias - 4u * m1b;
-                va = min3x2(max3x2(va, bias, bias), top, top) - bias;
-                vb = min3x2(max3x2(vb, bias, bias), top, top) - bias;
-                uint32_t l4 = __byte_perm(va, vb, 0x6420);
-                l4 = counts ? l4 : 0u;
+                va = max3x2(va, bias, va);  // the register twice: VIMNMX3 takes one immediate
+                vb = max3x2(vb, bias, vb);
+                va = min3x2(va, top, va);
+                vb = min3x2(vb, top, vb);
+                const uint32_t l4 = __byte_perm(va, vb, 0x6420) & count_mask;
                 sum = __dp4a(l4, 0x01010101u, sum);
                 sum2 = __dp4a(l4, l4, sum2);
             }
             m2a = m1a; m2b = m1b;
             m1a = ma; m1b = mb;
         }
-        a0 = b0; a1 = b1; a2 = b2; a3 = b3; a4 = b4;
-        b0 = c0; b1 = c1; b2 = c2; b3 = c3; b4 = c4;
-    }
+        a1 = b1; a2 = b2; a3 = b3; a4 = b4;
+        b1 = c1; b2 = c2; b3 = c3; b4 = c4;
+    };
+    using yes = std::true_type;
+    using no = std::false_type;
+    step(y0 - 2, no{}, no{});
+    step(y0 - 1, no{}, no{});
+    step(y0, yes{}, no{});
+    step(y0 + 1, yes{}, no{});
+#pragma unroll 6
+    for (int r = y0 + 2; r <= y1 + 1; ++r) step(r, yes{}, yes{});
 
     for (int off = 16; off > 0; off >>= 1) {
         sum += __shfl_down_sync(0xffffffffu, sum, off);
