@@ -150,6 +150,15 @@ def test_device_env_with_more_envs_than_one_scan_chunk(torch):
     assert _assert_same_rollout(host, device, actions) > 2500
 
 
+def test_device_env_with_70000_envs(torch):
+    """More envs than one grid row of the old stencil launch (65535) and restart ranks beyond
+    16 bits: 70 000 envs at 8x8 pixels, every env restarting at least once."""
+
+    host, device = _pair(70000, seed=36, frame_height=8, spp=2, max_steps=4)
+    actions = numpy.random.Generator(numpy.random.PCG64(7)).integers(0, 13, (6, 70000))
+    assert _assert_same_rollout(host, device, actions) > 70000
+
+
 def test_device_env_takes_device_actions_and_rejects_bad_ones(torch):
     _, device = _pair(4, seed=34, frame_height=32, spp=4)
     with pytest.raises(AssertionError):
