@@ -169,6 +169,26 @@ def test_multi_context_kernel_equals_literal_kernel(torch, contexts, height, n):
     numpy.testing.assert_array_equal(tested.context.rng_export(), literal.context.rng_export())
 
 
+@pytest.mark.parametrize("height,spp,n", [(1200, 2, 2), (601, 3, 1), (300, 100, 1)])
+def test_multi_context_kernel_at_sweep_sizes_matches_oracle(torch, height, spp, n):
+    """The 4-pixels-per-thread tracer at the sweep's frame sizes (and an odd one), gray path,
+    against the oracle: pixels and the RNG states left behind."""
+
+    from reinfocus_b200 import _lib
+
+    targets, planes = [6.25, 9.5][:n], [7.0, 9.0][:n]
+    gpu = _renderer(samples_per_pixel=spp)
+    gpu.context.set_option(_lib.OPT_TRACE_CONTEXTS, 4)
+    cpu = oracle.OracleFastRenderer(samples_per_pixel=spp, profile=oracle.PROFILE_GPU)
+    for renderer in (gpu, cpu):
+        renderer.update_targets(targets)
+        renderer.update_focus_planes(planes)
+    gray = gpu.render_gray_device(height).cpu().numpy()
+    assert gpu.context.last_trace_kernel() == 4
+    numpy.testing.assert_array_equal(gray, oracle.gray(cpu.render(height)))
+    numpy.testing.assert_array_equal(gpu.context.rng_export(), cpu.states)
+
+
 def test_pixels_per_thread_follow_the_batch_size(torch):
     """Default option: one pixel per thread for latency-bound small batches, four once
     the batch fills the GPU several times over; both leave the same frames as the oracle
