@@ -195,14 +195,21 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
         const size_t smem = (size_t)per_block * sizeof(rf::McSlots);
         switch (contexts) {
             case 2:
+                if (smem > 48 * 1024)
+                    RF_CUDA(ctx, cudaFuncSetAttribute(rf::trace_mc_kernel<2>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 rf::trace_mc_kernel<2><<<(unsigned)grid, rf::kMcThreads, smem, stream>>>(p, blocks_per_env);
                 break;
             case 4:
+                if (smem > 48 * 1024)
+                    RF_CUDA(ctx, cudaFuncSetAttribute(rf::trace_mc_kernel<4>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 rf::trace_mc_kernel<4><<<(unsigned)grid, rf::kMcThreads, smem, stream>>>(p, blocks_per_env);
                 break;
             case 8:
-                RF_CUDA(ctx, cudaFuncSetAttribute(rf::trace_mc_kernel<8>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (smem > 48 * 1024)
+                    RF_CUDA(ctx, cudaFuncSetAttribute(rf::trace_mc_kernel<8>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 rf::trace_mc_kernel<8><<<(unsigned)grid, rf::kMcThreads, smem, stream>>>(p, blocks_per_env);
                 break;
             default:
