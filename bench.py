@@ -147,7 +147,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -393,7 +393,7 @@ def run_ours(args):
     if os.path.exists(numba_path):
         with open(numba_path) as f:
             line["numba_cuda_baseline"] = json.load(f)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world_size > 1:
         dist.destroy_process_group()
 
@@ -412,6 +412,25 @@ def issue_view(traffic, n_local, trace_ms, sm_count, clock_summary):
             "ncu_pct": traffic.get("trace_kernel_ncu_pct")}
 
 
+_RESULT_STREAM = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything else that writes to file descriptor 1
+    (NCCL's version banner, library chatter) is sent to stderr for the life of the process."""
+
+    global _RESULT_STREAM
+    sys.stdout.flush()
+    _RESULT_STREAM = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    stream = _RESULT_STREAM or sys.stdout
+    stream.write(json.dumps(line) + "\n")
+    stream.flush()
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
@@ -424,6 +443,7 @@ def main():
                         help="pixels per thread of the tracer (0, 2, 4, 8); default: library default")
     args = parser.parse_args()
     assert args.warmup >= 1
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
