@@ -235,11 +235,23 @@ int launch_focus_packed(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, 
     p.W = W;
     p.channels = channels;
     p.segs = (W + rf::kPackedCols - 1) / rf::kPackedCols;
-    // rows per warp tile: 4 halo rows are recomputed per tile, so prefer tall tiles, but
-    // keep ~10 waves of 32 warps per SM so that the last wave's tail stays small
-    const int64_t want_tiles = (int64_t)ctx->prop.multiProcessorCount * 32 * 10;
+    // rows per warp tile. Each tile recomputes 4 halo rows, so tall tiles do less work, but
+    // the grid should fill the resident warps and come in enough waves that the last one's
+    // tail is small. Cost model, checked against measurements from 1 to 4096 envs:
+    // (1 + 4 / band) * (w >= 1 ? ceil(w) / w : 1 / w) with w = tiles / resident warps.
+    const double resident = (double)ctx->prop.multiProcessorCount * 32;
     int band = H;
-    while (band > 4 && (int64_t)n * p.segs * ((H + band - 1) / band) < want_tiles) band = (band + 1) / 2;
+    double best = 1e300;
+    for (int k = 1; k <= std::max(1, H / 4); ++k) {
+        const int rows = (H + k - 1) / k;
+        const double w = (double)n * p.segs * ((H + rows - 1) / rows) / resident;
+        const double fill = w >= 1.0 ? std::ceil(w) / w : 1.0 / w;
+        const double cost = (1.0 + 4.0 / rows) * fill;
+        if (cost < best - 1e-12) {
+            best = cost;
+            band = rows;
+        }
+    }
     p.band = band;
     p.bands = (H + band - 1) / band;
     // warps take tiles in one flat order over all envs, so blocks stay full whatever the
