@@ -1,5 +1,6 @@
 """Single-env Gymnasium environment composed of six strategy objects
-(reference environments/environment.py)."""
+(reference environments/environment.py). Internally it is a batch of one: the strategies
+are the vector ones, and this class unwraps their first row."""
 
 from typing import Any
 
@@ -8,49 +9,52 @@ import numpy
 from reinfocus_b200 import gym_compat
 
 
+def _first(*batched):
+    return tuple(values[0] for values in batched)
+
+
 class Environment(gym_compat.Env):
     # pylint: disable=too-many-instance-attributes
     """ender / initializer / observer / rewarder / transformer / visualizer, batch size 1
-    (reference :19-140)."""
+    (reference :19-140). Unlike the vector env it does not restart finished episodes: the
+    caller resets."""
 
     metadata = {"render_modes": ["rgb_array"], "render_fps": 4}
 
     def __init__(self, ender, initializer, observer, rewarder, transformer, visualizer,
                  render_mode: str | None = None):
         # pylint: disable=too-many-arguments
-        self._ender = ender
-        self._initializer = initializer
-        self._observer = observer
-        self._rewarder = rewarder
-        self._transformer = transformer
-        self._visualizer = visualizer
-        self.observation_space = observer.single_observation_space
+        self._ender, self._initializer, self._observer = ender, initializer, observer
+        self._rewarder, self._transformer, self._visualizer = rewarder, transformer, visualizer
         self.action_space = transformer.single_action_space
-        assert render_mode is None or render_mode in self.metadata["render_modes"]
+        self.observation_space = observer.single_observation_space
+        assert render_mode in (None, *self.metadata["render_modes"])
         self.render_mode = render_mode
         self._state = None
 
+    @property
+    def _drawing(self) -> bool:
+        return self.render_mode == "rgb_array"
+
     def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
         super().reset(seed=seed)
-        self._state = self._initializer.initialize(1)
-        self._ender.reset(self._state)
-        observations = self._observer.reset(self._state)
-        self._rewarder.reset(self._state, observations)
-        if self.render_mode == "rgb_array":
-            self._visualizer.reset(self._state, observations)
+        state = self._state = self._initializer.initialize(1)
+        self._ender.reset(state)
+        observations = self._observer.reset(state)
+        self._rewarder.reset(state, observations)
+        if self._drawing:
+            self._visualizer.reset(state, observations)
         return observations[0], {}
 
     def step(self, action):
         assert self._state is not None
-        self._state = self._transformer.transform(self._state, numpy.array([action]))
-        self._ender.step(self._state)
-        observations = self._observer.observe(self._state)
-        if self.render_mode == "rgb_array":
-            self._visualizer.step(self._state, observations)
-        return (observations[0], self._rewarder.reward(self._state, observations)[0],
-                self._ender.is_terminated()[0], self._ender.is_truncated()[0], {})
+        state = self._state = self._transformer.transform(self._state, numpy.array([action]))
+        self._ender.step(state)
+        observations = self._observer.observe(state)
+        if self._drawing:
+            self._visualizer.step(state, observations)
+        rewards = self._rewarder.reward(state, observations)
+        return (*_first(observations, rewards, self._ender.is_terminated(), self._ender.is_truncated()), {})
 
     def render(self):
-        if self.render_mode == "rgb_array":
-            return self._visualizer.visualize()
-        return None
+        return self._visualizer.visualize() if self._drawing else None

@@ -1,34 +1,37 @@
-"""Types shared by the strategy protocols (reference environments/types.py)."""
+"""Type vocabulary of the strategy protocols (reference environments/types.py): the batched
+state protocol and the state / action / observation type variables in their invariant,
+covariant and contravariant flavours."""
 
 from __future__ import annotations
 
-from typing import Generic, Protocol, TypeVar
+import typing
 
 import numpy
 from numpy.typing import NDArray
 
-T = TypeVar("T")
+T = typing.TypeVar("T")
+_Mask = NDArray[numpy.bool_]
 
 
-class IState(Protocol, Generic[T]):
+class IState(typing.Protocol, typing.Generic[T]):
     # pylint: disable=too-few-public-methods
-    """What a batched env state must support: boolean-mask reads and writes of sub-batches
-    (a NumPy array does)."""
+    """A batched env state: sub-batches are read and written through boolean masks over the
+    envs (a NumPy array qualifies)."""
 
-    def __getitem__(self, key: NDArray[numpy.bool_]) -> T:
-        ...
+    def __getitem__(self, key: _Mask) -> T: ...
 
-    def __setitem__(self, key: NDArray[numpy.bool_], value: T):
-        ...
+    def __setitem__(self, key: _Mask, value: T): ...
 
 
-StateT = TypeVar("StateT", bound=IState)
-StateT_co = TypeVar("StateT_co", bound=IState, covariant=True)
-StateT_contra = TypeVar("StateT_contra", bound=IState, contravariant=True)
+def _flavours(name: str, bound, invariant: bool = True):
+    made = []
+    if invariant:
+        made.append(typing.TypeVar(name, bound=bound))
+    made.append(typing.TypeVar(f"{name}_co", bound=bound, covariant=True))
+    made.append(typing.TypeVar(f"{name}_contra", bound=bound, contravariant=True))
+    return made
 
-ActionT = TypeVar("ActionT", bound=numpy.generic)
-ActionT_contra = TypeVar("ActionT_contra", bound=numpy.generic, contravariant=True)
 
-ObservationT = TypeVar("ObservationT", bound=numpy.generic)
-ObservationT_co = TypeVar("ObservationT_co", bound=numpy.generic, covariant=True)
-ObservationT_contra = TypeVar("ObservationT_contra", bound=numpy.generic, contravariant=True)
+StateT, StateT_co, StateT_contra = _flavours("StateT", IState)
+ActionT, _, ActionT_contra = _flavours("ActionT", numpy.generic)
+ObservationT, ObservationT_co, ObservationT_contra = _flavours("ObservationT", numpy.generic)

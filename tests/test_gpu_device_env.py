@@ -160,6 +160,15 @@ def test_device_env_with_70000_envs(torch):
 
 
 def test_device_env_takes_device_actions_and_rejects_bad_ones(torch):
+    # negative indices wrap around like NumPy's, int32 equals int64
+    host, twin = _pair(4, seed=37, frame_height=32, spp=4)
+    host.reset(), twin.reset()
+    for actions in ([-1, -13, 0, 5], [12, -7, -6, 3]):
+        want = host.step(numpy.array(actions))
+        got = twin.step(torch.tensor(actions, dtype=torch.int32, device="cuda"))
+        for w, g in zip(want[:4], got[:4]):
+            numpy.testing.assert_array_equal(g.cpu().numpy(), w)
+
     _, device = _pair(4, seed=34, frame_height=32, spp=4)
     with pytest.raises(AssertionError):
         device.step(numpy.zeros(4, dtype=numpy.int64))  # before reset
