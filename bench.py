@@ -440,7 +440,7 @@ def main():
     parser.add_argument("--impl", choices=["ours", "reference"], default="ours")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--contexts", type=int, default=None,
-                        help="pixels per thread of the tracer (0, 2, 4, 8); default: library default")
+                        help="pixels per thread of the tracer (0, 2..8); default: library default")
     args = parser.parse_args()
     assert args.warmup >= 1
     claim_stdout()

@@ -179,13 +179,14 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
     const bool fast = !ctx->force_generic && ctx->u[0] == 1.0f && ctx->u[1] == 0.0f &&
                       ctx->u[2] == 0.0f && ctx->v[0] == 0.0f && ctx->v[1] == 1.0f &&
                       ctx->v[2] == 0.0f && ctx->lens_radius == 0.05;
-    // four pixels per thread trade parallelism for fewer divergent rejection-loop trips:
-    // that pays once the batch fills every SM several times over (measured: from ~20 envs
-    // of 300x300 on; below that one pixel per thread has the lower step latency)
+    // several pixels per thread trade parallelism for fewer divergent rejection-loop trips:
+    // that pays once the batch fills every SM a few times over (measured: seven pixels per
+    // thread win from 16 envs of 300x300 on; below that one pixel per thread has the lower
+    // step latency)
     int contexts = ctx->trace_contexts;
     if (contexts < 0)
-        contexts = p.total >= (int64_t)ctx->prop.multiProcessorCount * 2048 * 6 ? 4 : 0;
-    if (!fast) contexts = 0;
+        contexts = p.total >= (int64_t)ctx->prop.multiProcessorCount * 9216 ? rf::kMcDefaultContexts : 0;
+    if (!fast || H > rf::kMcMaxFrame || W > rf::kMcMaxFrame) contexts = 0;
     if (contexts > 0) {
         // multi-context kernel: blocks are per env, kCtx * kMcThreads pixels each
         const int per_block = contexts * rf::kMcThreads;
@@ -193,28 +194,25 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
         const int64_t grid = (int64_t)n * blocks_per_env;
         if (grid > 0x7fffffffLL) return fail(ctx, RF_ERR_INVALID, "render batch too large");
         const size_t smem = (size_t)per_block * sizeof(rf::McSlots);
+        auto launch = [&](auto kernel) -> int {
+            if (smem > 48 * 1024)
+                RF_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kernel<<<(unsigned)grid, rf::kMcThreads, smem, stream>>>(p, blocks_per_env);
+            return RF_OK;
+        };
+        int rc = RF_OK;
         switch (contexts) {
-            case 2:
-                if (smem > 48 * 1024)
-                    RF_CUDA(ctx, cudaFuncSetAttribute(rf::trace_mc_kernel<2>,
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                rf::trace_mc_kernel<2><<<(unsigned)grid, rf::kMcThreads, smem, stream>>>(p, blocks_per_env);
-                break;
-            case 4:
-                if (smem > 48 * 1024)
-                    RF_CUDA(ctx, cudaFuncSetAttribute(rf::trace_mc_kernel<4>,
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                rf::trace_mc_kernel<4><<<(unsigned)grid, rf::kMcThreads, smem, stream>>>(p, blocks_per_env);
-                break;
-            case 8:
-                if (smem > 48 * 1024)
-                    RF_CUDA(ctx, cudaFuncSetAttribute(rf::trace_mc_kernel<8>,
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                rf::trace_mc_kernel<8><<<(unsigned)grid, rf::kMcThreads, smem, stream>>>(p, blocks_per_env);
-                break;
+            case 2: rc = launch(rf::trace_mc_kernel<2>); break;
+            case 3: rc = launch(rf::trace_mc_kernel<3>); break;
+            case 4: rc = launch(rf::trace_mc_kernel<4>); break;
+            case 5: rc = launch(rf::trace_mc_kernel<5>); break;
+            case 6: rc = launch(rf::trace_mc_kernel<6>); break;
+            case 7: rc = launch(rf::trace_mc_kernel<7>); break;
+            case 8: rc = launch(rf::trace_mc_kernel<8>); break;
             default:
                 return fail(ctx, RF_ERR_INVALID, "unsupported context count %d", contexts);
         }
+        if (rc) return rc;
     } else if (fast) {
         rf::trace_kernel<true><<<(unsigned)blocks, rf::kTraceThreads, 0, stream>>>(p);
     } else {
@@ -1007,8 +1005,8 @@ int rf_set_option(rf_ctx *ctx, int option, int value) {
             ctx->force_generic = value != 0;
             return RF_OK;
         case RF_OPT_TRACE_CONTEXTS:
-            if (value != -1 && value != 0 && value != 2 && value != 4 && value != 8)
-                return fail(ctx, RF_ERR_INVALID, "RF_OPT_TRACE_CONTEXTS must be -1, 0, 2, 4 or 8");
+            if (value != -1 && value != 0 && (value < 2 || value > 8))
+                return fail(ctx, RF_ERR_INVALID, "RF_OPT_TRACE_CONTEXTS must be -1, 0 or 2..8");
             ctx->trace_contexts = value;
             return RF_OK;
         default:

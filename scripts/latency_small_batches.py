@@ -20,7 +20,7 @@ def main():
     rng = numpy.random.Generator(numpy.random.PCG64DXSM(1234))
     for n in (1, 2, 4, 8, 13, 16, 32, 64):
         row = {"envs": n}
-        for contexts in (0, 2, 4):
+        for contexts in (0, 4, 7):
             renderer = render.FastRenderer()
             renderer.context.set_option(_lib.OPT_TRACE_CONTEXTS, contexts)
             targets = rng.uniform(5, 10, (12, n)).astype(numpy.float32)

@@ -144,7 +144,7 @@ def test_specialised_kernel_equals_literal_kernel(torch, targets, planes, height
     numpy.testing.assert_array_equal(fast.context.rng_export(), literal.context.rng_export())
 
 
-@pytest.mark.parametrize("contexts", [0, 2, 4, 8])
+@pytest.mark.parametrize("contexts", [0, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("height,n", [(36, 3), (50, 2), (75, 1)])
 def test_multi_context_kernel_equals_literal_kernel(torch, contexts, height, n):
     """Every pixels-per-thread setting of the default-camera kernel against the literal
@@ -171,27 +171,27 @@ def test_multi_context_kernel_equals_literal_kernel(torch, contexts, height, n):
 
 @pytest.mark.parametrize("height,spp,n", [(1200, 2, 2), (601, 3, 1), (300, 100, 1)])
 def test_multi_context_kernel_at_sweep_sizes_matches_oracle(torch, height, spp, n):
-    """The 4-pixels-per-thread tracer at the sweep's frame sizes (and an odd one), gray path,
+    """The 7-pixels-per-thread tracer at the sweep's frame sizes (and an odd one), gray path,
     against the oracle: pixels and the RNG states left behind."""
 
     from reinfocus_b200 import _lib
 
     targets, planes = [6.25, 9.5][:n], [7.0, 9.0][:n]
     gpu = _renderer(samples_per_pixel=spp)
-    gpu.context.set_option(_lib.OPT_TRACE_CONTEXTS, 4)
+    gpu.context.set_option(_lib.OPT_TRACE_CONTEXTS, 7)
     cpu = oracle.OracleFastRenderer(samples_per_pixel=spp, profile=oracle.PROFILE_GPU)
     for renderer in (gpu, cpu):
         renderer.update_targets(targets)
         renderer.update_focus_planes(planes)
     gray = gpu.render_gray_device(height).cpu().numpy()
-    assert gpu.context.last_trace_kernel() == 4
+    assert gpu.context.last_trace_kernel() == 7
     numpy.testing.assert_array_equal(gray, oracle.gray(cpu.render(height)))
     numpy.testing.assert_array_equal(gpu.context.rng_export(), cpu.states)
 
 
 def test_pixels_per_thread_follow_the_batch_size(torch):
-    """Default option: one pixel per thread for latency-bound small batches, four once
-    the batch fills the GPU several times over; both leave the same frames as the oracle
+    """Default option: one pixel per thread for latency-bound small batches, seven once
+    the batch fills the GPU a few times over; both leave the same frames as the oracle
     (covered above), here only the choice is checked."""
 
     small, large = _renderer(samples_per_pixel=1), _renderer(samples_per_pixel=1)
@@ -200,7 +200,7 @@ def test_pixels_per_thread_follow_the_batch_size(torch):
     assert small.context.last_trace_kernel() == 1
     large.update_targets([7.0] * 24), large.update_focus_planes([6.0] * 24)
     large.render_gray_device(300)
-    assert large.context.last_trace_kernel() == 4
+    assert large.context.last_trace_kernel() == 7
 
 
 def test_literal_kernel_handles_a_non_default_camera(torch):
@@ -393,7 +393,7 @@ def test_full_benchmark_batch_matches_oracle_on_sampled_envs(torch):
     sampled = [0, 1, 512, 513, 2047, 3333, 4095]
     before = {e: ctx.rng_export(e * pixels, pixels) for e in sampled}
     focus = renderer.step_focus(targets, planes, height)
-    assert ctx.last_trace_kernel() == 4 and ctx.last_focus_kernel() == 1
+    assert ctx.last_trace_kernel() == 7 and ctx.last_focus_kernel() == 1
     assert focus.shape == (n,) and numpy.isfinite(focus).all()
     world, cam = oracle.pack_world(targets), oracle.pack_cameras(planes)
     for e in sampled:
