@@ -324,7 +324,7 @@ def run_ours(args):
     base = cpu_baseline(max(1, min(args.steps, 2)), 1) if not args.no_cpu_baseline else None
 
     line = {
-        "metric": METRIC, "value": args.envs / (device_ms * 1e-3), "unit": UNIT,
+        "metric": METRIC if args.envs == 4096 else METRIC.replace("4096", str(args.envs)), "value": args.envs / (device_ms * 1e-3), "unit": UNIT,
         "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": device_ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32+f64+u64", "data": "synthetic",
