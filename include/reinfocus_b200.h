@@ -191,6 +191,8 @@ int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float 
  * (reference examples/custom_environments.py): state [target, focus plane];
  *   transformer  RF_ENV_DISCRETE_MOVE     DiscreteMoveTransformer (state_transformer.py:222-266)
  *                RF_ENV_CONTINUOUS_JUMP   ContinuousJumpTransformer (:88-137)
+ *                RF_ENV_CONTINUOUS_MOVE   ContinuousMoveTransformer (:140-192)
+ *                RF_ENV_DISCRETE_JUMP     DiscreteJumpTransformer (:195-219)
  *   ender        [TimeLimitEnder |] DivergingEnder (episode_ender.py:590-656, 112-207)
  *   observer     NormalizedObserver(DeltaObserver([IndexedElementObserver(plane),
  *                FocusObserver], include_original=True)) (state_observer.py:167-517)
@@ -205,7 +207,7 @@ int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float 
  * bit-identical to the host classes driven by the same generator.
  * ----------------------------------------------------------------------------------- */
 typedef struct rf_env rf_env;
-enum { RF_ENV_DISCRETE_MOVE = 0, RF_ENV_CONTINUOUS_JUMP = 1 };
+enum { RF_ENV_DISCRETE_MOVE = 0, RF_ENV_CONTINUOUS_JUMP = 1, RF_ENV_CONTINUOUS_MOVE = 2, RF_ENV_DISCRETE_JUMP = 3 };
 enum { RF_ENV_REWARD_STEPS = 0, RF_ENV_REWARD_JUMPS = 1 };
 enum { RF_ENV_ACTIONS_INT32 = 0, RF_ENV_ACTIONS_INT64 = 1, RF_ENV_ACTIONS_FLOAT32 = 2 };
 typedef struct {
@@ -215,7 +217,9 @@ typedef struct {
     double moves[32];        /* discrete action set, float64 as the reference keeps it */
     float limits[2];         /* clip range of the discrete move / ends of the jump */
     float jump_span;         /* float32(limits[1] - limits[0]) */
-    float jump_threshold;    /* jumps shorter than this are ignored */
+    float jump_threshold;    /* jumps / continuous moves shorter than this are ignored */
+    float move_speed;        /* RF_ENV_CONTINUOUS_MOVE: distance of action 1.0 */
+    float jumps[32];         /* RF_ENV_DISCRETE_JUMP: positions, float32 as the reference keeps them */
     int max_steps;           /* time limit, <= 0 for none */
     float diverge_threshold;
     int diverge_steps;

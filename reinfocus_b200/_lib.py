@@ -19,7 +19,7 @@ RF_ERR_CUDA = -2
 RF_ERR_NOMEM = -3
 RF_ERR_NO_SCENE = -4
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH, SELFTEST_CONST_DIV = 0, 1, 2, 3
 OPT_FORCE_GENERIC = 0
@@ -27,7 +27,7 @@ OPT_TRACE_CONTEXTS = 1
 INFO_LAST_TRACE_KERNEL = 0
 INFO_LAST_FOCUS_KERNEL = 1
 
-ENV_DISCRETE_MOVE, ENV_CONTINUOUS_JUMP = 0, 1
+ENV_DISCRETE_MOVE, ENV_CONTINUOUS_JUMP, ENV_CONTINUOUS_MOVE, ENV_DISCRETE_JUMP = 0, 1, 2, 3
 ENV_REWARD_STEPS, ENV_REWARD_JUMPS = 0, 1
 ENV_ACTIONS_INT32, ENV_ACTIONS_INT64, ENV_ACTIONS_FLOAT32 = 0, 1, 2
 
@@ -59,6 +59,8 @@ class EnvConfig(ctypes.Structure):
         ("limits", ctypes.c_float * 2),
         ("jump_span", ctypes.c_float),
         ("jump_threshold", ctypes.c_float),
+        ("move_speed", ctypes.c_float),
+        ("jumps", ctypes.c_float * 32),
         ("max_steps", ctypes.c_int),
         ("diverge_threshold", ctypes.c_float),
         ("diverge_steps", ctypes.c_int),

@@ -18,7 +18,7 @@
 #include "rf_rng.cuh"
 #include "rf_tracer.cuh"
 
-#define RF_ABI_VERSION 4
+#define RF_ABI_VERSION 5
 
 namespace {
 
@@ -773,11 +773,13 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
     RF_REQUIRE(ctx, c && out, "rf_env_create: NULL argument");
     RF_REQUIRE(ctx, c->num_envs > 0 && c->frame_height >= 2 && c->samples_per_pixel > 0,
                "rf_env_create: num_envs, frame_height and samples_per_pixel must be positive");
-    RF_REQUIRE(ctx, c->transformer == RF_ENV_DISCRETE_MOVE || c->transformer == RF_ENV_CONTINUOUS_JUMP,
+    RF_REQUIRE(ctx, c->transformer >= RF_ENV_DISCRETE_MOVE && c->transformer <= RF_ENV_DISCRETE_JUMP,
                "rf_env_create: unknown transformer %d", c->transformer);
     RF_REQUIRE(ctx, c->rewarder == RF_ENV_REWARD_STEPS || c->rewarder == RF_ENV_REWARD_JUMPS,
                "rf_env_create: unknown rewarder %d", c->rewarder);
-    RF_REQUIRE(ctx, c->transformer != RF_ENV_DISCRETE_MOVE || (c->n_moves > 0 && c->n_moves <= rf::kEnvMaxMoves),
+    RF_REQUIRE(ctx,
+               (c->transformer != RF_ENV_DISCRETE_MOVE && c->transformer != RF_ENV_DISCRETE_JUMP) ||
+                   (c->n_moves > 0 && c->n_moves <= rf::kEnvMaxMoves),
                "rf_env_create: a discrete action set holds 1..%d moves", rf::kEnvMaxMoves);
     RF_REQUIRE(ctx, c->diverge_steps > 0, "rf_env_create: diverge_steps must be positive");
     DeviceGuard guard(ctx->device);
@@ -791,6 +793,8 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
     p.transformer = c->transformer;
     p.n_moves = c->n_moves;
     for (int i = 0; i < rf::kEnvMaxMoves; ++i) p.moves[i] = i < c->n_moves ? c->moves[i] : 0.0;
+    for (int i = 0; i < rf::kEnvMaxMoves; ++i) p.jumps[i] = i < c->n_moves ? c->jumps[i] : 0.0f;
+    p.move_speed = c->move_speed;
     p.limit_lo = c->limits[0];
     p.limit_hi = c->limits[1];
     p.jump_span = c->jump_span;
@@ -936,7 +940,8 @@ int rf_env_step(rf_env *env, const void *d_actions, int action_kind, float *d_ob
     rf_ctx *ctx = env->ctx;
     RF_REQUIRE(ctx, env->started, "rf_env_step: reset the env first");
     RF_REQUIRE(ctx, d_actions && d_obs && d_rewards && d_truncated, "rf_env_step: NULL argument");
-    const bool discrete = env->params.transformer == rf::kEnvDiscreteMove;
+    const bool discrete = env->params.transformer == rf::kEnvDiscreteMove ||
+                          env->params.transformer == rf::kEnvDiscreteJump;
     RF_REQUIRE(ctx,
                discrete ? (action_kind == RF_ENV_ACTIONS_INT32 || action_kind == RF_ENV_ACTIONS_INT64)
                         : action_kind == RF_ENV_ACTIONS_FLOAT32,

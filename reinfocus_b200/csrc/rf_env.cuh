@@ -14,7 +14,7 @@
 
 namespace rf {
 
-enum { kEnvDiscreteMove = 0, kEnvContinuousJump = 1 };
+enum { kEnvDiscreteMove = 0, kEnvContinuousJump = 1, kEnvContinuousMove = 2, kEnvDiscreteJump = 3 };
 enum { kEnvRewardSteps = 0, kEnvRewardJumps = 1 };
 enum { kEnvActionsInt32 = 0, kEnvActionsInt64 = 1, kEnvActionsFloat32 = 2 };
 constexpr int kEnvMaxMoves = 32;
@@ -27,7 +27,9 @@ struct EnvParams {
     double moves[kEnvMaxMoves];  // DiscreteMoveTransformer keeps its action set in float64
     float limit_lo, limit_hi;
     float jump_span;             // float32(limits[1] - limits[0]), the difference taken in Python
-    float jump_threshold;
+    float jump_threshold;        // ContinuousJump / ContinuousMove: moves shorter than this are ignored
+    float move_speed;            // ContinuousMoveTransformer
+    float jumps[kEnvMaxMoves];   // DiscreteJumpTransformer keeps its action set in float32
     int max_steps;               // TimeLimitEnder; <= 0: none
     float diverge_threshold;     // DivergingEnder
     int diverge_steps;
@@ -138,6 +140,22 @@ env_pre_kernel(EnvParams p, EnvArrays a, const void *actions, int action_kind, i
                         action = 0;
                     }
                     plane = __double2float_rn(__dadd_rn((double)plane, p.moves[action]));
+                } else if (p.transformer == kEnvDiscreteJump) {
+                    // DiscreteJumpTransformer: the action picks the position (float32 set)
+                    long long action = action_kind == kEnvActionsInt64
+                                           ? ((const long long *)actions)[i]
+                                           : (long long)((const int *)actions)[i];
+                    if (action < 0) action += p.n_moves;
+                    if (action < 0 || action >= p.n_moves) {
+                        invalid = true;
+                        action = 0;
+                    }
+                    plane = p.jumps[action];
+                } else if (p.transformer == kEnvContinuousMove) {
+                    // ContinuousMoveTransformer: clip(a, -1, 1) * speed, ignored when shorter
+                    // than the stop threshold: state += (|move| > threshold) * move
+                    const float move = __fmul_rn(clip_f32(((const float *)actions)[i], -1.0f, 1.0f), p.move_speed);
+                    plane = __fadd_rn(plane, __fmul_rn(fabsf(move) > p.jump_threshold ? 1.0f : 0.0f, move));
                 } else {
                     // ContinuousJumpTransformer: ((a + 1) / 2) * (hi - lo) + lo, ignored when
                     // closer than the stop threshold
@@ -147,7 +165,7 @@ env_pre_kernel(EnvParams p, EnvArrays a, const void *actions, int action_kind, i
                         __fadd_rn(__fmul_rn(fraction, p.jump_span), p.limit_lo);
                     if (fabsf(__fsub_rn(plane, destination)) > p.jump_threshold) plane = destination;
                 }
-                if (p.transformer == kEnvDiscreteMove) {
+                if (p.transformer != kEnvContinuousJump) {  // the jump transformer does not clip
                     target = clip_f32(target, p.limit_lo, p.limit_hi);
                     plane = clip_f32(plane, p.limit_lo, p.limit_hi);
                 }

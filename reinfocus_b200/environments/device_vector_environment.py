@@ -12,7 +12,7 @@ Only the compositions of the example envs are understood (anything else raises
 ``NotImplementedError`` - use ``VectorEnvironment`` for it):
 
 * state ``[target, focus plane]``;
-* transformer ``DiscreteMoveTransformer`` or ``ContinuousJumpTransformer`` on the focus plane;
+* any of the four transformers (discrete / continuous, move / jump) on the focus plane;
 * ender ``DivergingEnder`` on (target, focus plane), optionally ``TimeLimitEnder | ...``;
 * observer ``NormalizedObserver(DeltaObserver([IndexedElementObserver(focus plane),
   FocusObserver], include_original=True, ...))``;
@@ -62,6 +62,18 @@ def _read_transformer(transformer, config: _lib.EnvConfig):
         config.transformer = _lib.ENV_CONTINUOUS_JUMP
         config.jump_span = _f32(transformer._limits[1] - transformer._limits[0])
         config.jump_threshold = _f32(transformer._stop_threshold)
+    elif isinstance(transformer, state_transformer.ContinuousMoveTransformer):
+        config.transformer = _lib.ENV_CONTINUOUS_MOVE
+        config.move_speed = _f32(transformer._speed)
+        config.jump_threshold = _f32(transformer._stop_threshold)
+    elif isinstance(transformer, state_transformer.DiscreteJumpTransformer):
+        positions = numpy.asarray(transformer._action_set, dtype=numpy.float32)
+        if len(positions) > 32:
+            _unsupported("transformer (more than 32 positions)")
+        config.transformer = _lib.ENV_DISCRETE_JUMP
+        config.n_moves = len(positions)
+        for i, position in enumerate(positions):
+            config.jumps[i] = float(position)
     else:
         _unsupported("transformer")
 
@@ -204,7 +216,7 @@ class DeviceVectorEnvironment(gym_compat.VectorEnv):
         config.packing = renderer.scene_packing()
 
         self._renderer = renderer
-        self._discrete = config.transformer == _lib.ENV_DISCRETE_MOVE
+        self._discrete = config.transformer in (_lib.ENV_DISCRETE_MOVE, _lib.ENV_DISCRETE_JUMP)
         self._device = torch.device(f"cuda:{renderer.context.device}")
         self._env = _lib.DeviceEnv(renderer.context, config)
         words = generator.bit_generator.state["state"]

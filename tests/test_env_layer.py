@@ -183,8 +183,13 @@ def test_device_env_refuses_compositions_it_does_not_implement(modules):
     assert (config.transformer, config.n_moves, list(config.moves[:3])) == (0, 3, [-1.0, 0.0, 1.0])
     dve._read_transformer(transformers.ContinuousJumpTransformer(2, 1, (5.0, 10.0), 0.125), config)
     assert (config.transformer, config.jump_span, config.jump_threshold) == (1, 5.0, 0.125)
+    dve._read_transformer(transformers.ContinuousMoveTransformer(2, 1, (5.0, 10.0), 1.5, 0.25), config)
+    assert (config.transformer, config.move_speed, config.jump_threshold) == (2, 1.5, 0.25)
+    dve._read_transformer(transformers.DiscreteJumpTransformer(2, 1, (5.0, 10.0), [5.0, 7.5, 10.0]), config)
+    assert (config.transformer, config.n_moves, list(config.jumps[:3])) == (3, 3, [5.0, 7.5, 10.0])
     for transformer in (transformers.DiscreteMoveTransformer(2, 0, (5.0, 10.0), [0.0]),
-                        transformers.ContinuousMoveTransformer(2, 1, (5.0, 10.0), 1.0),
+                        transformers.ContinuousMoveTransformer(2, 0, (5.0, 10.0), 1.0),
+                        transformers.DiscreteJumpTransformer(2, 1, (5.0, 10.0), numpy.zeros(33)),
                         transformers.DiscreteMoveTransformer(2, 1, (5.0, 10.0), numpy.zeros(33))):
         with pytest.raises(NotImplementedError):
             dve._read_transformer(transformer, config)

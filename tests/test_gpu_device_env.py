@@ -44,6 +44,14 @@ def _strategies(num_envs, renderer, seed, frame_height, kind="steps", max_steps=
             num_envs, 1, ENDS, numpy.concatenate([-moves, [0], moves[::-1]]))
         rewarder = (episode_rewarder.DeltaRewarder(1, 0.5) + episode_rewarder.ObservationRewarder(1)
                     + episode_rewarder.OnTargetRewarder((0, 1), 0.25))
+    elif kind in ("moves", "positions"):
+        if kind == "moves":
+            transformer = state_transformer.ContinuousMoveTransformer(num_envs, 1, ENDS, 2.5, 0.125)
+        else:
+            transformer = state_transformer.DiscreteJumpTransformer(
+                num_envs, 1, (5.5, 9.5), numpy.linspace(5.0, 10.0, 9))
+        rewarder = (episode_rewarder.DeltaRewarder(1, 0.5) + episode_rewarder.ObservationRewarder(1)
+                    + episode_rewarder.OnTargetRewarder((0, 1), 0.25))
     else:
         transformer = state_transformer.ContinuousJumpTransformer(num_envs, 1, ENDS, 0.125)
         rewarder = (episode_rewarder.ObservationRewarder(1)
@@ -138,6 +146,24 @@ def test_jump_device_env_equals_host_env(torch):
     raw = numpy.random.Generator(numpy.random.PCG64(4)).uniform(-1, 1, (50, 6, 1))
     raw[::4] *= 0.01
     actions = raw.astype(numpy.float32)
+    assert _assert_same_rollout(host, device, actions) > 0
+
+
+def test_continuous_move_device_env_equals_host_env(torch):
+    """ContinuousMoveTransformer: float32 actions beyond [-1, 1] (clipped), moves below the
+    stop threshold (ignored) and moves into the limits (clipped)."""
+
+    host, device = _pair(6, seed=38, frame_height=48, spp=8, kind="moves")
+    raw = numpy.random.Generator(numpy.random.PCG64(9)).uniform(-1.6, 1.6, (50, 6, 1))
+    raw[::3] *= 0.03
+    assert _assert_same_rollout(host, device, raw.astype(numpy.float32)) > 0
+
+
+def test_discrete_jump_device_env_equals_host_env(torch):
+    """DiscreteJumpTransformer: positions from a float32 set, some outside the clip limits."""
+
+    host, device = _pair(6, seed=39, frame_height=48, spp=8, kind="positions")
+    actions = numpy.random.Generator(numpy.random.PCG64(10)).integers(0, 9, (50, 6))
     assert _assert_same_rollout(host, device, actions) > 0
 
 
