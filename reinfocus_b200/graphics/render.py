@@ -205,18 +205,19 @@ class FastRenderer:
             # first use: the statics (origin, u, v, lens) travel by value with
             # rf_set_cameras; afterwards only the dynamic part is copied, inside rf_step_host
             self._ctx.set_cameras(cam_data, *self._cameras.statics)
-        key = n
-        bufs = self._pinned.get(key)
-        if bufs is None:
-            bufs = (torch.empty((n, 2), dtype=torch.float32).pin_memory(),
-                    torch.empty((n, 9), dtype=torch.float32).pin_memory(),
-                    torch.empty((n,), dtype=torch.float64).pin_memory())
-            self._pinned = {key: bufs}
-        h_world, h_cam, h_focus = bufs
+        # pinned staging buffers, grown on demand and reused for smaller batches (the vector
+        # env alternates between all n envs and the k that restarted)
+        if self._pinned.get("capacity", 0) < n:
+            capacity = max(n, 2 * self._pinned.get("capacity", 0))
+            self._pinned = {"capacity": capacity,
+                            "world": torch.empty((capacity, 2), dtype=torch.float32).pin_memory(),
+                            "cameras": torch.empty((capacity, 9), dtype=torch.float32).pin_memory(),
+                            "focus": torch.empty((capacity,), dtype=torch.float64).pin_memory()}
+        h_world, h_cam, h_focus = (self._pinned[name][:n] for name in ("world", "cameras", "focus"))
         if upload_world:
             h_world.numpy()[...] = world_data
         if upload_cameras:
-            h_cam.numpy()[...] = cam_data.reshape(n, 9)
+            h_cam.numpy()[...] = cam_data[:n].reshape(n, 9)
         self._ctx.step_host(n, frame_height, self._samples_per_pixel,
                             h_world.data_ptr() if upload_world else None,
                             h_cam.data_ptr() if upload_cameras else None,
