@@ -324,4 +324,6 @@ def train(num_envs: int = 8, rollouts: int = 2, config: PPOConfig | None = None,
         history.append(entry)
         if rank == 0:
             log(entry)
+    if world > 1:
+        torch.distributed.destroy_process_group()
     return history
