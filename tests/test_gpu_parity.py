@@ -189,6 +189,37 @@ def test_multi_context_kernel_at_sweep_sizes_matches_oracle(torch, height, spp, 
     numpy.testing.assert_array_equal(gpu.context.rng_export(), cpu.states)
 
 
+def test_frames_beyond_the_multi_pixel_kernels_coordinate_range(torch):
+    """The multi-pixel tracer keeps pixel coordinates as half floats (exact below 2048); a
+    2052-pixel frame must take the one-pixel kernel, whatever the option says, and match the
+    oracle."""
+
+    from reinfocus_b200 import _lib
+
+    height, spp = 2052, 1
+    gpu = _renderer(samples_per_pixel=spp)
+    gpu.context.set_option(_lib.OPT_TRACE_CONTEXTS, 7)
+    cpu = oracle.OracleFastRenderer(samples_per_pixel=spp, profile=oracle.PROFILE_GPU)
+    for renderer in (gpu, cpu):
+        renderer.update_targets([8.0])
+        renderer.update_focus_planes([7.0])
+    gray = gpu.render_gray_device(height).cpu().numpy()
+    assert gpu.context.last_trace_kernel() == 1
+    numpy.testing.assert_array_equal(gray, oracle.gray(cpu.render(height)))
+    # 2048 itself is inside the range: the largest frame of the multi-pixel kernel
+    edge = _renderer(samples_per_pixel=spp)
+    edge.context.set_option(_lib.OPT_TRACE_CONTEXTS, 7)
+    edge_cpu = oracle.OracleFastRenderer(samples_per_pixel=spp, profile=oracle.PROFILE_GPU)
+    for renderer in (edge, edge_cpu):
+        renderer.update_targets([8.0])
+        renderer.update_focus_planes([7.0])
+    gray = edge.render_gray_device(2048).cpu().numpy()
+    assert edge.context.last_trace_kernel() == 7
+    numpy.testing.assert_array_equal(gray, oracle.gray(edge_cpu.render(2048)))
+    with pytest.raises(AssertionError):
+        edge.context.set_option(_lib.OPT_TRACE_CONTEXTS, 9)
+
+
 def test_pixels_per_thread_follow_the_batch_size(torch):
     """Default option: one pixel per thread for latency-bound small batches, seven once
     the batch fills the GPU a few times over; both leave the same frames as the oracle
