@@ -193,12 +193,15 @@ int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float 
  *                RF_ENV_CONTINUOUS_JUMP   ContinuousJumpTransformer (:88-137)
  *                RF_ENV_CONTINUOUS_MOVE   ContinuousMoveTransformer (:140-192)
  *                RF_ENV_DISCRETE_JUMP     DiscreteJumpTransformer (:195-219)
- *   ender        [TimeLimitEnder |] DivergingEnder (episode_ender.py:590-656, 112-207)
+ *   ender        any tree of TimeLimitEnder, DivergingEnder, OnTargetEnder, StoppedEnder,
+ *                EndlessEnder combined with & and | (episode_ender.py:112-656), given as a
+ *                postfix program of rf_env_ender nodes
  *   observer     NormalizedObserver(DeltaObserver([IndexedElementObserver(plane),
  *                FocusObserver], include_original=True)) (state_observer.py:167-517)
- *   rewarder     RF_ENV_REWARD_STEPS  DeltaRewarder + ObservationRewarder(1) + OnTargetRewarder
- *                RF_ENV_REWARD_JUMPS  ObservationRewarder(1) + StoppedRewarder * OnTargetRewarder
- *                (episode_rewarder.py:86-429)
+ *   rewarder     any tree of DeltaRewarder, DistanceRewarder, ObservationRewarder,
+ *                OnTargetRewarder, StoppedRewarder combined with + and *
+ *                (episode_rewarder.py:86-429), as a postfix program of rf_env_reward nodes;
+ *                NumPy's result types are followed (float32 until a float64 operand joins)
  *   initializer  RangedInitializer, one range per element, numpy PCG64DXSM generator
  *                (state_initializer.py:30-71)
  * States, observations, rewards and the generator live on the GPU; a step is two small
@@ -208,7 +211,25 @@ int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float 
  * ----------------------------------------------------------------------------------- */
 typedef struct rf_env rf_env;
 enum { RF_ENV_DISCRETE_MOVE = 0, RF_ENV_CONTINUOUS_JUMP = 1, RF_ENV_CONTINUOUS_MOVE = 2, RF_ENV_DISCRETE_JUMP = 3 };
-enum { RF_ENV_REWARD_STEPS = 0, RF_ENV_REWARD_JUMPS = 1 };
+enum { RF_ENV_ENDER_TIME_LIMIT = 0, RF_ENV_ENDER_DIVERGING = 1, RF_ENV_ENDER_ON_TARGET = 2,
+       RF_ENV_ENDER_STOPPED = 3, RF_ENV_ENDER_ENDLESS = 4, RF_ENV_ENDER_AND = 5, RF_ENV_ENDER_OR = 6 };
+enum { RF_ENV_REWARD_DELTA = 0, RF_ENV_REWARD_DISTANCE = 1, RF_ENV_REWARD_OBSERVATION = 2,
+       RF_ENV_REWARD_ON_TARGET = 3, RF_ENV_REWARD_STOPPED = 4, RF_ENV_REWARD_ADD = 5, RF_ENV_REWARD_MUL = 6 };
+/* One node of the ender program. i0 / i1: the state elements it looks at; steps: max_steps
+ * (time limit) or early_end_steps (<= 15 for STOPPED); value: threshold / radius / span. */
+typedef struct {
+    int kind, i0, i1, steps;
+    float value;
+} rf_env_ender;
+/* One node of the rewarder program. DELTA: i0, f0 = reward, f1 = scale. DISTANCE: i0, i1,
+ * f0 = span, f1 = float32(high - low), d0 = low. OBSERVATION: i0 = observation column.
+ * ON_TARGET: i0, i1, f0 = span, d0 = off, d1 = on - off. STOPPED: i0, f0 = threshold,
+ * d0 = reward. */
+typedef struct {
+    int kind, i0, i1;
+    float f0, f1;
+    double d0, d1;
+} rf_env_reward;
 enum { RF_ENV_ACTIONS_INT32 = 0, RF_ENV_ACTIONS_INT64 = 1, RF_ENV_ACTIONS_FLOAT32 = 2 };
 typedef struct {
     int num_envs, frame_height, samples_per_pixel;
@@ -220,15 +241,9 @@ typedef struct {
     float jump_threshold;    /* jumps / continuous moves shorter than this are ignored */
     float move_speed;        /* RF_ENV_CONTINUOUS_MOVE: distance of action 1.0 */
     float jumps[32];         /* RF_ENV_DISCRETE_JUMP: positions, float32 as the reference keeps them */
-    int max_steps;           /* time limit, <= 0 for none */
-    float diverge_threshold;
-    int diverge_steps;
-    int rewarder;
-    float delta_reward, delta_scale;
-    float stop_threshold;
-    double stop_reward;
-    float on_span;
-    double on_off, on_delta;
+    int n_enders, n_rewards; /* program lengths, 1..8 each */
+    rf_env_ender enders[8];
+    rf_env_reward rewards[8];
     float obs_mid[4], obs_scale[4]; /* NormalizedObserver._mid / ._scale */
     double init_low[2], init_high[2];
     rf_scene_packing packing;
@@ -250,13 +265,12 @@ int rf_env_step(rf_env *env, const void *d_actions, int action_kind, float *d_ob
  * checkpoint / resume; the reference cannot serialise an env). Together with the generator
  * (rf_env_get/set_generator) and the renderer's RNG states (rf_rng_export/import) this is
  * everything a resumed run needs to continue bit-identically. h_states float32 [n, 2],
- * h_steps / h_diverging int32 [n], h_last_gap float32 [n] (DivergingEnder), h_old_obs
- * float32 [n, 2] (DeltaObserver), h_old_plane float32 [n] (Delta / Stopped rewarder). Export
+ * h_old_obs float32 [n, 2] (DeltaObserver), h_node_state uint32 [rf_env_node_rows(env), n]
+ * (the enders' counters / windows and the rewarders' previous values, raw bits). Export
  * skips NULL pointers; import needs all of them and stands in for a reset. */
-int rf_env_export(rf_env *env, float *h_states, int *h_steps, int *h_diverging, float *h_last_gap,
-                  float *h_old_obs, float *h_old_plane);
-int rf_env_import(rf_env *env, const float *h_states, const int *h_steps, const int *h_diverging,
-                  const float *h_last_gap, const float *h_old_obs, const float *h_old_plane);
+int rf_env_node_rows(const rf_env *env);
+int rf_env_export(rf_env *env, float *h_states, float *h_old_obs, uint32_t *h_node_state);
+int rf_env_import(rf_env *env, const float *h_states, const float *h_old_obs, const uint32_t *h_node_state);
 
 /* -------------------------------------------------------------------------------------
  * Self-checks and measurement helpers (used by tests/ and bench.py).

@@ -19,7 +19,7 @@ RF_ERR_CUDA = -2
 RF_ERR_NOMEM = -3
 RF_ERR_NO_SCENE = -4
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH, SELFTEST_CONST_DIV = 0, 1, 2, 3
 OPT_FORCE_GENERIC = 0
@@ -28,7 +28,12 @@ INFO_LAST_TRACE_KERNEL = 0
 INFO_LAST_FOCUS_KERNEL = 1
 
 ENV_DISCRETE_MOVE, ENV_CONTINUOUS_JUMP, ENV_CONTINUOUS_MOVE, ENV_DISCRETE_JUMP = 0, 1, 2, 3
-ENV_REWARD_STEPS, ENV_REWARD_JUMPS = 0, 1
+(ENV_ENDER_TIME_LIMIT, ENV_ENDER_DIVERGING, ENV_ENDER_ON_TARGET, ENV_ENDER_STOPPED, ENV_ENDER_ENDLESS,
+ ENV_ENDER_AND, ENV_ENDER_OR) = range(7)
+(ENV_REWARD_DELTA, ENV_REWARD_DISTANCE, ENV_REWARD_OBSERVATION, ENV_REWARD_ON_TARGET, ENV_REWARD_STOPPED,
+ ENV_REWARD_ADD, ENV_REWARD_MUL) = range(7)
+ENV_MAX_NODES = 8
+ENV_MAX_WINDOW = 16
 ENV_ACTIONS_INT32, ENV_ACTIONS_INT64, ENV_ACTIONS_FLOAT32 = 0, 1, 2
 
 STATE_DTYPE = numpy.dtype([("s0", numpy.uint64), ("s1", numpy.uint64)], align=True)
@@ -47,6 +52,21 @@ class ScenePacking(ctypes.Structure):
     ]
 
 
+class EnvEnder(ctypes.Structure):
+    """rf_env_ender."""
+
+    _fields_ = [("kind", ctypes.c_int), ("i0", ctypes.c_int), ("i1", ctypes.c_int),
+                ("steps", ctypes.c_int), ("value", ctypes.c_float)]
+
+
+class EnvReward(ctypes.Structure):
+    """rf_env_reward."""
+
+    _fields_ = [("kind", ctypes.c_int), ("i0", ctypes.c_int), ("i1", ctypes.c_int),
+                ("f0", ctypes.c_float), ("f1", ctypes.c_float),
+                ("d0", ctypes.c_double), ("d1", ctypes.c_double)]
+
+
 class EnvConfig(ctypes.Structure):
     """rf_env_config."""
 
@@ -61,15 +81,9 @@ class EnvConfig(ctypes.Structure):
         ("jump_threshold", ctypes.c_float),
         ("move_speed", ctypes.c_float),
         ("jumps", ctypes.c_float * 32),
-        ("max_steps", ctypes.c_int),
-        ("diverge_threshold", ctypes.c_float),
-        ("diverge_steps", ctypes.c_int),
-        ("rewarder", ctypes.c_int),
-        ("delta_reward", ctypes.c_float), ("delta_scale", ctypes.c_float),
-        ("stop_threshold", ctypes.c_float),
-        ("stop_reward", ctypes.c_double),
-        ("on_span", ctypes.c_float),
-        ("on_off", ctypes.c_double), ("on_delta", ctypes.c_double),
+        ("n_enders", ctypes.c_int), ("n_rewards", ctypes.c_int),
+        ("enders", EnvEnder * 8),
+        ("rewards", EnvReward * 8),
         ("obs_mid", ctypes.c_float * 4), ("obs_scale", ctypes.c_float * 4),
         ("init_low", ctypes.c_double * 2), ("init_high", ctypes.c_double * 2),
         ("packing", ScenePacking),
@@ -120,8 +134,9 @@ _SIGNATURES = {
     "rf_env_reset": (ctypes.c_int, [_vp, _vp, _vp]),
     "rf_env_step": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp, _vp,
                                    ctypes.POINTER(ctypes.c_int), _vp]),
-    "rf_env_export": (ctypes.c_int, [_vp] + [_vp] * 6),
-    "rf_env_import": (ctypes.c_int, [_vp] + [_vp] * 6),
+    "rf_env_node_rows": (ctypes.c_int, [_vp]),
+    "rf_env_export": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "rf_env_import": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "rf_selftest": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int,
                                    ctypes.POINTER(ctypes.c_int64), _vp]),
     "rf_set_option": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
@@ -417,26 +432,27 @@ class DeviceEnv:
                                           _stream_ptr(stream, self._context.device)))
         return resets.value
 
-    _EXPORT_LAYOUT = (("states", numpy.float32, 2), ("steps", numpy.int32, 1),
-                      ("diverging", numpy.int32, 1), ("last_gap", numpy.float32, 1),
-                      ("old_obs", numpy.float32, 2), ("old_plane", numpy.float32, 1))
+    def _layout(self):
+        rows = int(self._lib.rf_env_node_rows(self._handle))
+        return (("states", numpy.float32, (self.num_envs, 2)), ("old_obs", numpy.float32, (self.num_envs, 2)),
+                ("node_state", numpy.uint32, (rows, self.num_envs)))
 
     def export(self) -> dict:
-        """Host copies of the per-env episode state."""
+        """Host copies of the per-env episode state: states, the DeltaObserver's previous
+        observations and the raw per-env rows of the ender / rewarder nodes."""
 
-        arrays = {name: numpy.empty((self.num_envs, width) if width > 1 else self.num_envs, dtype=dtype)
-                  for name, dtype, width in self._EXPORT_LAYOUT}
+        arrays = {name: numpy.empty(shape, dtype=dtype) for name, dtype, shape in self._layout()}
         self._check(self._lib.rf_env_export(
-            self._handle, *[arrays[name].ctypes.data for name, _, _ in self._EXPORT_LAYOUT]))
+            self._handle, *[arrays[name].ctypes.data for name, _, _ in self._layout()]))
         return arrays
 
     def load(self, arrays: dict):
         """Restores what ``export`` returned (stands in for a reset)."""
 
         ordered = []
-        for name, dtype, width in self._EXPORT_LAYOUT:
+        for name, dtype, shape in self._layout():
             array = numpy.ascontiguousarray(arrays[name], dtype=dtype)
-            assert array.shape == ((self.num_envs, width) if width > 1 else (self.num_envs,)), name
+            assert array.shape == shape, name
             ordered.append(array)
         self._check(self._lib.rf_env_import(self._handle, *[array.ctypes.data for array in ordered]))
 

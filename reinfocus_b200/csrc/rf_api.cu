@@ -18,7 +18,7 @@
 #include "rf_rng.cuh"
 #include "rf_tracer.cuh"
 
-#define RF_ABI_VERSION 5
+#define RF_ABI_VERSION 6
 
 namespace {
 
@@ -738,7 +738,7 @@ struct rf_env {
     rf_ctx *ctx = nullptr;
     rf::EnvParams params{};
     rf_scene_packing packing{};
-    int H = 0, spp = 0;
+    int H = 0, spp = 0, node_rows = 0;
     rf::EnvArrays arrays{};
     double *d_focus_main = nullptr, *d_focus_reset = nullptr;
     int *h_counters = nullptr;  // pinned [2]
@@ -753,11 +753,8 @@ int rf_env_destroy(rf_env *env) {
     cudaFree(a.states);
     cudaFree(a.new_states);
     cudaFree(a.reset_rank);
-    cudaFree(a.steps);
-    cudaFree(a.diverging);
-    cudaFree(a.last_gap);
     cudaFree(a.old_obs);
-    cudaFree(a.old_plane);
+    cudaFree(a.node_state);
     cudaFree(a.generator);
     cudaFree(a.counters);
     cudaFree(env->d_focus_main);
@@ -775,13 +772,13 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
                "rf_env_create: num_envs, frame_height and samples_per_pixel must be positive");
     RF_REQUIRE(ctx, c->transformer >= RF_ENV_DISCRETE_MOVE && c->transformer <= RF_ENV_DISCRETE_JUMP,
                "rf_env_create: unknown transformer %d", c->transformer);
-    RF_REQUIRE(ctx, c->rewarder == RF_ENV_REWARD_STEPS || c->rewarder == RF_ENV_REWARD_JUMPS,
-               "rf_env_create: unknown rewarder %d", c->rewarder);
+    RF_REQUIRE(ctx, c->n_enders >= 1 && c->n_enders <= rf::kEnvMaxNodes && c->n_rewards >= 1 &&
+                        c->n_rewards <= rf::kEnvMaxNodes,
+               "rf_env_create: ender / rewarder programs hold 1..%d nodes", rf::kEnvMaxNodes);
     RF_REQUIRE(ctx,
                (c->transformer != RF_ENV_DISCRETE_MOVE && c->transformer != RF_ENV_DISCRETE_JUMP) ||
                    (c->n_moves > 0 && c->n_moves <= rf::kEnvMaxMoves),
                "rf_env_create: a discrete action set holds 1..%d moves", rf::kEnvMaxMoves);
-    RF_REQUIRE(ctx, c->diverge_steps > 0, "rf_env_create: diverge_steps must be positive");
     DeviceGuard guard(ctx->device);
     rf_env *env = new rf_env();
     env->ctx = ctx;
@@ -799,17 +796,53 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
     p.limit_hi = c->limits[1];
     p.jump_span = c->jump_span;
     p.jump_threshold = c->jump_threshold;
-    p.max_steps = c->max_steps;
-    p.diverge_threshold = c->diverge_threshold;
-    p.diverge_steps = c->diverge_steps;
-    p.rewarder = c->rewarder;
-    p.delta_reward = c->delta_reward;
-    p.delta_scale = c->delta_scale;
-    p.stop_threshold = c->stop_threshold;
-    p.stop_reward = c->stop_reward;
-    p.on_span = c->on_span;
-    p.on_off = c->on_off;
-    p.on_delta = c->on_delta;
+    // the programs: check that they are well-formed postfix expressions over state indices
+    // 0 / 1, and give every node its per-env state rows
+    int rows = 0, depth = 0;
+    p.n_enders = c->n_enders;
+    for (int k = 0; k < c->n_enders; ++k) {
+        const rf_env_ender &src = c->enders[k];
+        rf::EnderNode &node = p.enders[k];
+        node = rf::EnderNode{src.kind, src.i0, src.i1, src.steps, src.value, rows};
+        const bool leaf = src.kind >= RF_ENV_ENDER_TIME_LIMIT && src.kind <= RF_ENV_ENDER_ENDLESS;
+        const bool op = src.kind == RF_ENV_ENDER_AND || src.kind == RF_ENV_ENDER_OR;
+        const bool indices_ok = src.i0 >= 0 && src.i0 <= 1 && src.i1 >= 0 && src.i1 <= 1;
+        if (!(leaf || op) || !indices_ok || (op && depth < 2) ||
+            (src.kind == RF_ENV_ENDER_STOPPED && (src.steps < 1 || src.steps + 1 > rf::kEnvMaxWindow))) {
+            delete env;
+            return fail(ctx, RF_ERR_INVALID, "rf_env_create: malformed ender program at node %d", k);
+        }
+        depth += leaf ? 1 : -1;
+        if (src.kind == RF_ENV_ENDER_TIME_LIMIT || src.kind == RF_ENV_ENDER_ON_TARGET) rows += 1;
+        if (src.kind == RF_ENV_ENDER_DIVERGING) rows += 2;
+        if (src.kind == RF_ENV_ENDER_STOPPED) rows += src.steps + 2;
+    }
+    if (depth != 1) {
+        delete env;
+        return fail(ctx, RF_ERR_INVALID, "rf_env_create: the ender program does not reduce to one value");
+    }
+    depth = 0;
+    p.n_rewards = c->n_rewards;
+    for (int k = 0; k < c->n_rewards; ++k) {
+        const rf_env_reward &src = c->rewards[k];
+        rf::RewardNode &node = p.rewards[k];
+        node = rf::RewardNode{src.kind, src.i0, src.i1, rows, src.f0, src.f1, src.d0, src.d1};
+        const bool leaf = src.kind >= RF_ENV_REWARD_DELTA && src.kind <= RF_ENV_REWARD_STOPPED;
+        const bool op = src.kind == RF_ENV_REWARD_ADD || src.kind == RF_ENV_REWARD_MUL;
+        const int max_index = src.kind == RF_ENV_REWARD_OBSERVATION ? 3 : 1;
+        const bool indices_ok = src.i0 >= 0 && src.i0 <= max_index && src.i1 >= 0 && src.i1 <= 1;
+        if (!(leaf || op) || !indices_ok || (op && depth < 2)) {
+            delete env;
+            return fail(ctx, RF_ERR_INVALID, "rf_env_create: malformed rewarder program at node %d", k);
+        }
+        depth += leaf ? 1 : -1;
+        if (src.kind == RF_ENV_REWARD_DELTA || src.kind == RF_ENV_REWARD_STOPPED) rows += 1;
+    }
+    if (depth != 1) {
+        delete env;
+        return fail(ctx, RF_ERR_INVALID, "rf_env_create: the rewarder program does not reduce to one value");
+    }
+    env->node_rows = std::max(rows, 1);
     for (int i = 0; i < 4; ++i) {
         p.obs_mid[i] = c->obs_mid[i];
         p.obs_scale[i] = c->obs_scale[i];
@@ -826,10 +859,9 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
     };
     const bool ok = alloc((void **)&a.states, sizeof(float) * 2 * n) &&
                     alloc((void **)&a.new_states, sizeof(float) * 2 * n) &&
-                    alloc((void **)&a.reset_rank, sizeof(int) * n) && alloc((void **)&a.steps, sizeof(int) * n) &&
-                    alloc((void **)&a.diverging, sizeof(int) * n) && alloc((void **)&a.last_gap, sizeof(float) * n) &&
+                    alloc((void **)&a.reset_rank, sizeof(int) * n) &&
                     alloc((void **)&a.old_obs, sizeof(float) * 2 * n) &&
-                    alloc((void **)&a.old_plane, sizeof(float) * n) &&
+                    alloc((void **)&a.node_state, sizeof(uint32_t) * n * (size_t)env->node_rows) &&
                     alloc((void **)&a.generator, sizeof(uint64_t) * 4) &&
                     alloc((void **)&a.counters, sizeof(int) * 2) &&
                     alloc((void **)&env->d_focus_main, sizeof(double) * n) &&
@@ -954,8 +986,7 @@ int rf_env_step(rf_env *env, const void *d_actions, int action_kind, float *d_ob
 namespace {
 
 // host <-> device copies of the per-env arrays (to_host or from host)
-int env_copy_arrays(rf_env *env, bool to_host, float *h_states, int *h_steps, int *h_diverging,
-                    float *h_last_gap, float *h_old_obs, float *h_old_plane) {
+int env_copy_arrays(rf_env *env, bool to_host, float *h_states, float *h_old_obs, uint32_t *h_node_state) {
     rf_ctx *ctx = env->ctx;
     DeviceGuard guard(ctx->device);
     const size_t n = (size_t)env->params.n;
@@ -966,9 +997,9 @@ int env_copy_arrays(rf_env *env, bool to_host, float *h_states, int *h_steps, in
         void *device;
         size_t bytes;
     } items[] = {
-        {h_states, a.states, sizeof(float) * 2 * n},     {h_steps, a.steps, sizeof(int) * n},
-        {h_diverging, a.diverging, sizeof(int) * n},     {h_last_gap, a.last_gap, sizeof(float) * n},
-        {h_old_obs, a.old_obs, sizeof(float) * 2 * n},   {h_old_plane, a.old_plane, sizeof(float) * n},
+        {h_states, a.states, sizeof(float) * 2 * n},
+        {h_old_obs, a.old_obs, sizeof(float) * 2 * n},
+        {h_node_state, a.node_state, sizeof(uint32_t) * n * (size_t)env->node_rows},
     };
     for (const Item &item : items) {
         if (!item.host) continue;
@@ -982,20 +1013,18 @@ int env_copy_arrays(rf_env *env, bool to_host, float *h_states, int *h_steps, in
 
 }  // namespace
 
-int rf_env_export(rf_env *env, float *h_states, int *h_steps, int *h_diverging, float *h_last_gap,
-                  float *h_old_obs, float *h_old_plane) {
+int rf_env_node_rows(const rf_env *env) { return env ? env->node_rows : 0; }
+
+int rf_env_export(rf_env *env, float *h_states, float *h_old_obs, uint32_t *h_node_state) {
     if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_export: env is NULL");
-    return env_copy_arrays(env, true, h_states, h_steps, h_diverging, h_last_gap, h_old_obs, h_old_plane);
+    return env_copy_arrays(env, true, h_states, h_old_obs, h_node_state);
 }
 
-int rf_env_import(rf_env *env, const float *h_states, const int *h_steps, const int *h_diverging,
-                  const float *h_last_gap, const float *h_old_obs, const float *h_old_plane) {
+int rf_env_import(rf_env *env, const float *h_states, const float *h_old_obs, const uint32_t *h_node_state) {
     if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_import: env is NULL");
-    RF_REQUIRE(env->ctx, h_states && h_steps && h_diverging && h_last_gap && h_old_obs && h_old_plane,
-               "rf_env_import: every array is required");
-    if (int rc = env_copy_arrays(env, false, const_cast<float *>(h_states), const_cast<int *>(h_steps),
-                                 const_cast<int *>(h_diverging), const_cast<float *>(h_last_gap),
-                                 const_cast<float *>(h_old_obs), const_cast<float *>(h_old_plane)))
+    RF_REQUIRE(env->ctx, h_states && h_old_obs && h_node_state, "rf_env_import: every array is required");
+    if (int rc = env_copy_arrays(env, false, const_cast<float *>(h_states), const_cast<float *>(h_old_obs),
+                                 const_cast<uint32_t *>(h_node_state)))
         return rc;
     env->started = true;  // the imported episode state stands in for a reset
     return RF_OK;

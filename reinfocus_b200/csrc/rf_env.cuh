@@ -15,14 +15,36 @@
 namespace rf {
 
 enum { kEnvDiscreteMove = 0, kEnvContinuousJump = 1, kEnvContinuousMove = 2, kEnvDiscreteJump = 3 };
-enum { kEnvRewardSteps = 0, kEnvRewardJumps = 1 };
 enum { kEnvActionsInt32 = 0, kEnvActionsInt64 = 1, kEnvActionsFloat32 = 2 };
+// ender / rewarder expression trees, flattened to postfix programs
+enum { kEnderTimeLimit = 0, kEnderDiverging = 1, kEnderOnTarget = 2, kEnderStopped = 3, kEnderEndless = 4,
+       kEnderAnd = 5, kEnderOr = 6 };
+enum { kRewardDelta = 0, kRewardDistance = 1, kRewardObservation = 2, kRewardOnTarget = 3, kRewardStopped = 4,
+       kRewardAdd = 5, kRewardMul = 6 };
 constexpr int kEnvMaxMoves = 32;
+constexpr int kEnvMaxNodes = 8;
+constexpr int kEnvMaxWindow = 16;  // StoppedEnder: early_end_steps + 1 positions
 constexpr int kEnvPreThreads = 1024;
+
+struct EnderNode {
+    int kind;
+    int i0, i1;    // state indices it looks at
+    int steps;     // TimeLimit: max_steps; Diverging / OnTarget / Stopped: early_end_steps
+    float value;   // Diverging: threshold; OnTarget: radius; Stopped: span
+    int slot;      // first of its per-env state rows in EnvArrays::node_state
+};
+
+struct RewardNode {
+    int kind;
+    int i0, i1;        // state indices (Observation: the observation column)
+    int slot;          // Delta / Stopped: the row with the previous value of state[i0]
+    float f0, f1;      // Delta: reward, scale; Distance: span, float32(high - low); Stopped: threshold
+    double d0, d1;     // Distance: low; OnTarget: off, delta; Stopped: reward
+};
 
 struct EnvParams {
     int n;
-    int transformer;             // kEnvDiscreteMove | kEnvContinuousJump
+    int transformer;             // kEnvDiscreteMove ... kEnvDiscreteJump
     int n_moves;
     double moves[kEnvMaxMoves];  // DiscreteMoveTransformer keeps its action set in float64
     float limit_lo, limit_hi;
@@ -30,16 +52,10 @@ struct EnvParams {
     float jump_threshold;        // ContinuousJump / ContinuousMove: moves shorter than this are ignored
     float move_speed;            // ContinuousMoveTransformer
     float jumps[kEnvMaxMoves];   // DiscreteJumpTransformer keeps its action set in float32
-    int max_steps;               // TimeLimitEnder; <= 0: none
-    float diverge_threshold;     // DivergingEnder
-    int diverge_steps;
-    int rewarder;                // kEnvRewardSteps | kEnvRewardJumps
-    float delta_reward, delta_scale;  // DeltaRewarder
-    float stop_threshold;             // StoppedRewarder
-    double stop_reward;
-    float on_span;                    // OnTargetRewarder
-    double on_off, on_delta;
-    float obs_mid[4], obs_scale[4];   // NormalizedObserver
+    int n_enders, n_rewards;
+    EnderNode enders[kEnvMaxNodes];
+    RewardNode rewards[kEnvMaxNodes];
+    float obs_mid[4], obs_scale[4];     // NormalizedObserver
     double init_low[2], init_range[2];  // RangedInitializer, one range per element
 };
 
@@ -47,11 +63,8 @@ struct EnvArrays {
     float *states;        // [n, 2]  target, focus plane
     float *new_states;    // [n, 2]  first states of restarted episodes, by reset rank
     int *reset_rank;      // [n]     position among this step's restarted envs, -1 if none
-    int *steps;           // [n]     TimeLimitEnder
-    int *diverging;       // [n]     DivergingEnder
-    float *last_gap;      // [n]
     float *old_obs;       // [n, 2]  DeltaObserver: previous [focus plane, focus value]
-    float *old_plane;     // [n]     Delta / Stopped rewarder: previous focus plane
+    uint32_t *node_state; // [rows, n] per-env state of the ender / rewarder nodes (int or float bits)
     uint64_t *generator;  // [4]     PCG64DXSM state hi, lo, increment hi, lo
     int *counters;        // [2]     number of restarted envs, invalid-action flag
 };
@@ -103,6 +116,160 @@ __device__ inline float env_gap(float target, float plane) { return fabsf(__fsub
 __device__ inline float normalized(const EnvParams &p, int column, float value) {
     // NormalizedObserver._normalize: clip((values - mid) / scale, -1, 1)
     return clip_f32(__fdiv_rn(__fsub_rn(value, p.obs_mid[column]), p.obs_scale[column]), -1.0f, 1.0f);
+}
+
+// per-env state rows of the strategy nodes
+__device__ inline int &node_int(const EnvArrays &a, int n, int row, int env) {
+    return reinterpret_cast<int *>(a.node_state)[(size_t)row * n + env];
+}
+__device__ inline float &node_float(const EnvArrays &a, int n, int row, int env) {
+    return reinterpret_cast<float *>(a.node_state)[(size_t)row * n + env];
+}
+
+// ender.step(states) for every node, then is_truncated() of the tree (nothing ever
+// terminates: reference episode_ender.py:92-98). Postfix evaluation on a small stack.
+__device__ inline bool enders_step(const EnvParams &p, const EnvArrays &a, int env, const float *state) {
+    bool stack[kEnvMaxNodes];
+    int top = 0;
+    for (int k = 0; k < p.n_enders; ++k) {
+        const EnderNode &node = p.enders[k];
+        switch (node.kind) {
+            case kEnderTimeLimit: {  // episode_ender.py:590-656
+                const int steps = ++node_int(a, p.n, node.slot, env);
+                stack[top++] = steps >= node.steps;
+                break;
+            }
+            case kEnderDiverging: {  // :112-207: the gap grew by more than the threshold
+                const float gap = env_gap(state[node.i0], state[node.i1]);
+                int &count = node_int(a, p.n, node.slot, env);
+                float &last = node_float(a, p.n, node.slot + 1, env);
+                if (gap > __fadd_rn(last, node.value)) ++count;
+                last = gap;
+                stack[top++] = count >= node.steps;
+                break;
+            }
+            case kEnderOnTarget: {  // :273-369: consecutive steps within the radius
+                int &count = node_int(a, p.n, node.slot, env);
+                count = env_gap(state[node.i0], state[node.i1]) < node.value ? count + 1 : 0;
+                stack[top++] = count >= node.steps;
+                break;
+            }
+            case kEnderStopped: {  // :466-587: span of the last steps + 1 positions
+                const int window = node.steps + 1;
+                int &filled = node_int(a, p.n, node.slot, env);
+                for (int j = 0; j + 1 < window; ++j)
+                    node_float(a, p.n, node.slot + 1 + j, env) = node_float(a, p.n, node.slot + 2 + j, env);
+                node_float(a, p.n, node.slot + window, env) = state[node.i0];
+                filled = min(filled + 1, window);
+                float lo = state[node.i0], hi = lo;
+                for (int j = 0; j < window; ++j) {
+                    const float v = node_float(a, p.n, node.slot + 1 + j, env);
+                    lo = fminf(lo, v);  // rows not filled yet hold NaN: ignored like nanmin / nanmax
+                    hi = fmaxf(hi, v);
+                }
+                stack[top++] = filled >= window && fabsf(__fsub_rn(hi, lo)) < node.value;
+                break;
+            }
+            case kEnderEndless:
+                stack[top++] = false;
+                break;
+            case kEnderAnd:
+                --top;
+                stack[top - 1] = stack[top - 1] & stack[top];
+                break;
+            default:  // kEnderOr
+                --top;
+                stack[top - 1] = stack[top - 1] | stack[top];
+                break;
+        }
+    }
+    return stack[0];
+}
+
+// ender.reset(new_state, done) for one restarted env
+__device__ inline void enders_reset(const EnvParams &p, const EnvArrays &a, int env, const float *state) {
+    for (int k = 0; k < p.n_enders; ++k) {
+        const EnderNode &node = p.enders[k];
+        if (node.kind == kEnderTimeLimit || node.kind == kEnderOnTarget) {
+            node_int(a, p.n, node.slot, env) = 0;
+        } else if (node.kind == kEnderDiverging) {
+            node_int(a, p.n, node.slot, env) = 0;
+            node_float(a, p.n, node.slot + 1, env) = env_gap(state[node.i0], state[node.i1]);
+        } else if (node.kind == kEnderStopped) {
+            const int window = node.steps + 1;
+            for (int j = 0; j + 1 < window; ++j) node_float(a, p.n, node.slot + 1 + j, env) = __int_as_float(0x7fc00000);
+            node_float(a, p.n, node.slot + window, env) = state[node.i0];
+            node_int(a, p.n, node.slot, env) = 1;
+        }
+    }
+}
+
+// rewarder.reward(states, observations): postfix evaluation with NumPy's result types - a
+// value is float32 until a float64 operand (bool * Python float) joins it
+struct RewardValue {
+    double value;
+    bool wide;
+};
+
+__device__ inline RewardValue rewards_eval(const EnvParams &p, const EnvArrays &a, int env, const float *state,
+                                            const float *obs) {
+    RewardValue stack[kEnvMaxNodes];
+    int top = 0;
+    for (int k = 0; k < p.n_rewards; ++k) {
+        const RewardNode &node = p.rewards[k];
+        switch (node.kind) {
+            case kRewardDelta: {  // episode_rewarder.py:86-156: |x - previous| * reward / scale
+                float &previous = node_float(a, p.n, node.slot, env);
+                const float moved = fabsf(__fsub_rn(state[node.i0], previous));
+                previous = state[node.i0];
+                stack[top++] = {(double)__fdiv_rn(__fmul_rn(moved, node.f0), node.f1), false};
+                break;
+            }
+            case kRewardDistance: {  // :159-207: (1 - gap / span) * (high - low) + low
+                const float gap = env_gap(state[node.i0], state[node.i1]);
+                const float unit = __fsub_rn(1.0f, __fdiv_rn(gap, node.f0));
+                stack[top++] = {(double)__fadd_rn(__fmul_rn(unit, node.f1), (float)node.d0), false};
+                break;
+            }
+            case kRewardObservation:  // :210-238
+                stack[top++] = {(double)obs[node.i0], false};
+                break;
+            case kRewardOnTarget:  // :241-292: bool * Python float -> float64
+                stack[top++] = {__dadd_rn(env_gap(state[node.i0], state[node.i1]) < node.f0 ? node.d1 : 0.0, node.d0),
+                                true};
+                break;
+            case kRewardStopped: {  // :361-429
+                float &previous = node_float(a, p.n, node.slot, env);
+                const float moved = fabsf(__fsub_rn(state[node.i0], previous));
+                previous = state[node.i0];
+                stack[top++] = {moved < node.f0 ? node.d0 : 0.0, true};
+                break;
+            }
+            default: {  // kRewardAdd / kRewardMul
+                --top;
+                RewardValue &l = stack[top - 1];
+                const RewardValue r = stack[top];
+                if (l.wide || r.wide) {
+                    l.value = node.kind == kRewardAdd ? __dadd_rn(l.value, r.value) : __dmul_rn(l.value, r.value);
+                    l.wide = true;
+                } else {
+                    l.value = node.kind == kRewardAdd ? (double)__fadd_rn((float)l.value, (float)r.value)
+                                                      : (double)__fmul_rn((float)l.value, (float)r.value);
+                }
+                break;
+            }
+        }
+    }
+    return stack[0];
+}
+
+// rewarder.reset(new_state, new_observations, done) for one restarted env
+__device__ inline void rewards_reset(const EnvParams &p, const EnvArrays &a, int env, const float *state) {
+    for (int k = 0; k < p.n_rewards; ++k) {
+        const RewardNode &node = p.rewards[k];
+        if (node.kind == kRewardDelta || node.kind == kRewardStopped)
+            node_float(a, p.n, node.slot, env) = state[node.i0];
+    }
 }
 
 // --------------------------------------------------------------------------- step, part 1
@@ -171,14 +338,8 @@ env_pre_kernel(EnvParams p, EnvArrays a, const void *actions, int action_kind, i
                 }
                 a.states[2 * i] = target;
                 a.states[2 * i + 1] = plane;
-                // ender.step, then is_truncated
-                const int steps = a.steps[i] + 1;
-                a.steps[i] = steps;
-                const float gap = env_gap(target, plane);
-                int diverging = a.diverging[i];
-                if (gap > __fadd_rn(a.last_gap[i], p.diverge_threshold)) a.diverging[i] = ++diverging;
-                a.last_gap[i] = gap;
-                done = (p.max_steps > 0 && steps >= p.max_steps) || diverging >= p.diverge_steps;
+                const float state[2] = {target, plane};
+                done = enders_step(p, a, i, state);
             }
         }
         // ordered rank of the restarted envs
@@ -247,21 +408,8 @@ __global__ void env_post_kernel(EnvParams p, EnvArrays a, const double *focus_ma
         a.old_obs[2 * i] = plane;
         a.old_obs[2 * i + 1] = value;
 
-        const float moved = fabsf(__fsub_rn(plane, a.old_plane[i]));
-        a.old_plane[i] = plane;
-        const double on_target =
-            __dadd_rn(env_gap(target, plane) < p.on_span ? p.on_delta : 0.0, p.on_off);
-        double reward;
-        if (p.rewarder == kEnvRewardSteps) {
-            // (DeltaRewarder + ObservationRewarder(1)) + OnTargetRewarder: float32 + float32,
-            // then float64 because bool * Python float is float64
-            const float travel = __fdiv_rn(__fmul_rn(moved, p.delta_reward), p.delta_scale);
-            reward = __dadd_rn((double)__fadd_rn(travel, out[1]), on_target);
-        } else {
-            // ObservationRewarder(1) + (StoppedRewarder * OnTargetRewarder)
-            const double stopped = moved < p.stop_threshold ? p.stop_reward : 0.0;
-            reward = __dadd_rn((double)out[1], __dmul_rn(stopped, on_target));
-        }
+        const float state[2] = {target, plane};
+        const double reward = rewards_eval(p, a, i, state, out).value;
         rewards[i] = reward;
         truncated[i] = rank >= 0;
     }
@@ -270,13 +418,12 @@ __global__ void env_post_kernel(EnvParams p, EnvArrays a, const double *focus_ma
         const float target = a.new_states[2 * rank], plane = a.new_states[2 * rank + 1];
         a.states[2 * i] = target;
         a.states[2 * i + 1] = plane;
-        a.steps[i] = 0;
-        a.diverging[i] = 0;
-        a.last_gap[i] = env_gap(target, plane);
+        const float state[2] = {target, plane};
+        enders_reset(p, a, i, state);
+        rewards_reset(p, a, i, state);
         const float value = __double2float_rn(focus_reset[rank]);
         a.old_obs[2 * i] = plane;
         a.old_obs[2 * i + 1] = value;
-        a.old_plane[i] = plane;
         out[0] = normalized(p, 0, plane);
         out[1] = normalized(p, 1, value);
         out[2] = normalized(p, 2, 0.0f);  // DeltaObserver emits zero changes on reset

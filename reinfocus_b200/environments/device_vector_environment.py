@@ -8,16 +8,16 @@ observations and rewards live in device memory and a policy on the GPU can act o
 without a host round trip. Sequences are bit-identical to ``VectorEnvironment`` driven by the
 same generator (tests/test_gpu_device_env.py).
 
-Only the compositions of the example envs are understood (anything else raises
-``NotImplementedError`` - use ``VectorEnvironment`` for it):
+What is understood (anything else raises ``NotImplementedError`` - use ``VectorEnvironment``):
 
 * state ``[target, focus plane]``;
 * any of the four transformers (discrete / continuous, move / jump) on the focus plane;
-* ender ``DivergingEnder`` on (target, focus plane), optionally ``TimeLimitEnder | ...``;
+* any ``&`` / ``|`` tree of ``TimeLimitEnder``, ``DivergingEnder``, ``OnTargetEnder``,
+  ``StoppedEnder``, ``EndlessEnder`` (up to 8 nodes);
 * observer ``NormalizedObserver(DeltaObserver([IndexedElementObserver(focus plane),
   FocusObserver], include_original=True, ...))``;
-* rewarder ``DeltaRewarder + ObservationRewarder(1) + OnTargetRewarder`` or
-  ``ObservationRewarder(1) + StoppedRewarder * OnTargetRewarder``;
+* any ``+`` / ``*`` tree of ``DeltaRewarder``, ``DistanceRewarder``, ``ObservationRewarder``,
+  ``OnTargetRewarder``, ``StoppedRewarder`` (up to 8 nodes), with NumPy's result types;
 * initializer ``RangedInitializer`` with one range per element and a PCG64DXSM generator.
 """
 
@@ -78,71 +78,105 @@ def _read_transformer(transformer, config: _lib.EnvConfig):
         _unsupported("transformer")
 
 
+def _state_index(index) -> int:
+    index = int(index)
+    if index not in (TARGET, FOCUS_PLANE):
+        _unsupported("strategy (the state is [target, focus plane])")
+    return index
+
+
 def _read_ender(ender, config: _lib.EnvConfig):
+    """Flattens the ender tree into the postfix program of rf_env_config."""
+
     # pylint: disable=protected-access
-    config.max_steps = 0
-    if isinstance(ender, episode_ender.OpEnder):
-        if ender._op is not numpy.bitwise_or:
-            _unsupported("ender (only | is supported)")
-        pair = (ender._l_ender, ender._r_ender)
-        limits = [e for e in pair if isinstance(e, episode_ender.TimeLimitEnder)]
-        others = [e for e in pair if not isinstance(e, episode_ender.TimeLimitEnder)]
-        if len(limits) != 1 or len(others) != 1:
+    program: list[_lib.EnvEnder] = []
+
+    def emit(node):
+        if isinstance(node, episode_ender.OpEnder):
+            kinds = {numpy.bitwise_and: _lib.ENV_ENDER_AND, numpy.bitwise_or: _lib.ENV_ENDER_OR}
+            if node._op not in kinds:
+                _unsupported("ender (only & and | combine enders)")
+            emit(node._l_ender)
+            emit(node._r_ender)
+            program.append(_lib.EnvEnder(kinds[node._op], 0, 0, 0, 0.0))
+        elif isinstance(node, episode_ender.TimeLimitEnder):
+            program.append(_lib.EnvEnder(_lib.ENV_ENDER_TIME_LIMIT, 0, 0, int(node._max_steps), 0.0))
+        elif isinstance(node, episode_ender.DivergingEnder):
+            a, b = (_state_index(i) for i in node._check_indices)
+            program.append(_lib.EnvEnder(_lib.ENV_ENDER_DIVERGING, a, b, int(node._early_end_steps),
+                                         _f32(node._threshold)))
+        elif isinstance(node, episode_ender.OnTargetEnder):
+            a, b = (_state_index(i) for i in node._check_indices)
+            program.append(_lib.EnvEnder(_lib.ENV_ENDER_ON_TARGET, a, b, int(node._early_end_steps),
+                                         _f32(node._radius)))
+        elif isinstance(node, episode_ender.StoppedEnder):
+            if node._early_end_steps + 1 > _lib.ENV_MAX_WINDOW:
+                _unsupported(f"ender (StoppedEnder windows hold at most {_lib.ENV_MAX_WINDOW} positions)")
+            program.append(_lib.EnvEnder(_lib.ENV_ENDER_STOPPED, _state_index(node._check_index), 0,
+                                         int(node._early_end_steps), _f32(node._early_end_span)))
+        elif isinstance(node, episode_ender.EndlessEnder):
+            program.append(_lib.EnvEnder(_lib.ENV_ENDER_ENDLESS, 0, 0, 0, 0.0))
+        else:
             _unsupported("ender")
-        config.max_steps = int(limits[0]._max_steps)
-        ender = others[0]
-    if not isinstance(ender, episode_ender.DivergingEnder):
-        _unsupported("ender")
-    if tuple(ender._check_indices) not in ((TARGET, FOCUS_PLANE), (FOCUS_PLANE, TARGET)):
-        _unsupported("ender (it must compare target and focus plane)")
-    config.diverge_threshold = _f32(ender._threshold)
-    config.diverge_steps = int(ender._early_end_steps)
+
+    emit(ender)
+    if len(program) > _lib.ENV_MAX_NODES:
+        _unsupported(f"ender (more than {_lib.ENV_MAX_NODES} nodes)")
+    config.n_enders = len(program)
+    for i, node in enumerate(program):
+        config.enders[i] = node
 
 
-def _read_on_target(rewarder, config: _lib.EnvConfig):
+def _read_rewarder(rewarder, config: _lib.EnvConfig) -> bool:
+    """Flattens the rewarder tree into the postfix program of rf_env_config. Returns whether
+    NumPy would make the rewards float64 (a float32 tree stays float32)."""
+
     # pylint: disable=protected-access
-    if not isinstance(rewarder, episode_rewarder.OnTargetRewarder) or tuple(
-            rewarder._check_indices) not in ((TARGET, FOCUS_PLANE), (FOCUS_PLANE, TARGET)):
+    program: list[_lib.EnvReward] = []
+
+    def emit(node) -> bool:
+        if isinstance(node, episode_rewarder.OpRewarder):
+            kinds = {numpy.add: _lib.ENV_REWARD_ADD, numpy.multiply: _lib.ENV_REWARD_MUL}
+            if node._op not in kinds:
+                _unsupported("rewarder (only + and * combine rewarders)")
+            wide_l = emit(node._l_rewarder)
+            wide_r = emit(node._r_rewarder)
+            program.append(_lib.EnvReward(kinds[node._op], 0, 0, 0.0, 0.0, 0.0, 0.0))
+            return wide_l or wide_r
+        if isinstance(node, episode_rewarder.DeltaRewarder):
+            program.append(_lib.EnvReward(_lib.ENV_REWARD_DELTA, _state_index(node._check_index), 0,
+                                          _f32(node._reward), _f32(node._scale), 0.0, 0.0))
+            return False
+        if isinstance(node, episode_rewarder.DistanceRewarder):
+            a, b = (_state_index(i) for i in node._check_indices)
+            program.append(_lib.EnvReward(_lib.ENV_REWARD_DISTANCE, a, b, _f32(node._span),
+                                          _f32(node._high - node._low), float(node._low), 0.0))
+            return False
+        if isinstance(node, episode_rewarder.ObservationRewarder):
+            column = int(node._reward_observation_index)
+            if not 0 <= column < 4:
+                _unsupported("rewarder (observation column out of range)")
+            program.append(_lib.EnvReward(_lib.ENV_REWARD_OBSERVATION, column, 0, 0.0, 0.0, 0.0, 0.0))
+            return False
+        if isinstance(node, episode_rewarder.OnTargetRewarder):
+            a, b = (_state_index(i) for i in node._check_indices)
+            program.append(_lib.EnvReward(_lib.ENV_REWARD_ON_TARGET, a, b, _f32(node._span), 0.0,
+                                          float(node._off), float(node._delta)))
+            return True
+        if isinstance(node, episode_rewarder.StoppedRewarder):
+            program.append(_lib.EnvReward(_lib.ENV_REWARD_STOPPED, _state_index(node._check_index), 0,
+                                          _f32(node._threshold), 0.0, float(node._reward), 0.0))
+            return True
         _unsupported("rewarder")
-    config.on_span = _f32(rewarder._span)
-    config.on_off = float(rewarder._off)
-    config.on_delta = float(rewarder._delta)
+        return False
 
-
-def _is_focus_reward(rewarder) -> bool:
-    # pylint: disable=protected-access
-    return (isinstance(rewarder, episode_rewarder.ObservationRewarder)
-            and rewarder._reward_observation_index == 1)
-
-
-def _read_rewarder(rewarder, config: _lib.EnvConfig):
-    # pylint: disable=protected-access
-    def op(node, ufunc):
-        return isinstance(node, episode_rewarder.OpRewarder) and node._op is ufunc
-
-    if op(rewarder, numpy.add) and op(rewarder._l_rewarder, numpy.add):
-        # (DeltaRewarder + ObservationRewarder(1)) + OnTargetRewarder
-        delta, focus = rewarder._l_rewarder._l_rewarder, rewarder._l_rewarder._r_rewarder
-        if not (isinstance(delta, episode_rewarder.DeltaRewarder)
-                and delta._check_index == FOCUS_PLANE and _is_focus_reward(focus)):
-            _unsupported("rewarder")
-        config.rewarder = _lib.ENV_REWARD_STEPS
-        config.delta_reward = _f32(delta._reward)
-        config.delta_scale = _f32(delta._scale)
-        _read_on_target(rewarder._r_rewarder, config)
-    elif op(rewarder, numpy.add) and op(rewarder._r_rewarder, numpy.multiply):
-        # ObservationRewarder(1) + (StoppedRewarder * OnTargetRewarder)
-        stopped = rewarder._r_rewarder._l_rewarder
-        if not (_is_focus_reward(rewarder._l_rewarder)
-                and isinstance(stopped, episode_rewarder.StoppedRewarder)
-                and stopped._check_index == FOCUS_PLANE):
-            _unsupported("rewarder")
-        config.rewarder = _lib.ENV_REWARD_JUMPS
-        config.stop_threshold = _f32(stopped._threshold)
-        config.stop_reward = float(stopped._reward)
-        _read_on_target(rewarder._r_rewarder._r_rewarder, config)
-    else:
-        _unsupported("rewarder")
+    wide = emit(rewarder)
+    if len(program) > _lib.ENV_MAX_NODES:
+        _unsupported(f"rewarder (more than {_lib.ENV_MAX_NODES} nodes)")
+    config.n_rewards = len(program)
+    for i, node in enumerate(program):
+        config.rewards[i] = node
+    return wide
 
 
 def _read_observer(observer, config: _lib.EnvConfig):
@@ -209,7 +243,7 @@ class DeviceVectorEnvironment(gym_compat.VectorEnv):
         config.num_envs = num_envs
         _read_transformer(transformer, config)
         _read_ender(ender, config)
-        _read_rewarder(rewarder, config)
+        self._wide_rewards = _read_rewarder(rewarder, config)
         renderer = _read_observer(observer, config)
         generator = _read_initializer(initializer, config)
         config.samples_per_pixel = renderer.samples_per_pixel
@@ -247,6 +281,8 @@ class DeviceVectorEnvironment(gym_compat.VectorEnv):
         self._renderer.scene_overwritten()
         self.last_resets = self._env.step(actions.data_ptr(), kind, observations.data_ptr(),
                                           rewards.data_ptr(), truncated.data_ptr())
+        if not self._wide_rewards:
+            rewards = rewards.to(torch.float32)  # exact: a float32 tree was evaluated in float32
         return observations, rewards, terminated, truncated, {}
 
     def close(self, **kwargs):

@@ -140,41 +140,49 @@ def test_sb3_adapter_follows_the_vec_env_protocol(modules):
         assert vector_shim.rewrapper(marker) is marker
 
 
-def test_device_env_refuses_compositions_it_does_not_implement(modules):
-    """DeviceVectorEnvironment reads the parameters of a fixed menu of strategy compositions;
-    anything else must raise instead of being approximated."""
+def test_device_env_reads_strategy_trees_and_refuses_the_rest(modules):
+    """DeviceVectorEnvironment flattens the ender / rewarder trees into postfix programs and
+    reads the other strategies' parameters; what it cannot express must raise instead of
+    being approximated."""
 
     from reinfocus_b200 import _lib
     from reinfocus_b200.environments import device_vector_environment as dve
 
     m = modules
     config = _lib.EnvConfig()
-    time_limit = m.episode_ender.TimeLimitEnder(2, 20)
-    diverging = m.episode_ender.DivergingEnder(2, (0, 1), 0.125, early_end_steps=3)
+    enders = m.episode_ender
+    time_limit = enders.TimeLimitEnder(2, 20)
+    diverging = enders.DivergingEnder(2, (0, 1), 0.125, early_end_steps=3)
     dve._read_ender(time_limit | diverging, config)
-    assert (config.max_steps, config.diverge_steps, config.diverge_threshold) == (20, 3, 0.125)
-    dve._read_ender(diverging, config)
-    assert config.max_steps == 0
-    for ender in (time_limit & diverging, time_limit, m.episode_ender.OnTargetEnder(2, (0, 1), 0.4),
-                  m.episode_ender.DivergingEnder(2, (0, 0), 0.1)):
+    kinds = [config.enders[i].kind for i in range(config.n_enders)]
+    assert kinds == [_lib.ENV_ENDER_TIME_LIMIT, _lib.ENV_ENDER_DIVERGING, _lib.ENV_ENDER_OR]
+    assert (config.enders[0].steps, config.enders[1].steps, config.enders[1].value) == (20, 3, 0.125)
+    tree = (enders.OnTargetEnder(2, (0, 1), 0.4, early_end_steps=2)
+            | enders.StoppedEnder(2, 1, 0.05, early_end_steps=3)) & (enders.EndlessEnder(2) | time_limit)
+    dve._read_ender(tree, config)
+    kinds = [config.enders[i].kind for i in range(config.n_enders)]
+    assert kinds == [_lib.ENV_ENDER_ON_TARGET, _lib.ENV_ENDER_STOPPED, _lib.ENV_ENDER_OR,
+                     _lib.ENV_ENDER_ENDLESS, _lib.ENV_ENDER_TIME_LIMIT, _lib.ENV_ENDER_OR, _lib.ENV_ENDER_AND]
+    for ender in (enders.DivergingEnder(2, (0, 2), 0.1), enders.StoppedEnder(2, 1, 0.05, early_end_steps=16),
+                  enders.OpEnder(time_limit, diverging, numpy.bitwise_xor),
+                  time_limit | time_limit | time_limit | time_limit | time_limit):
         with pytest.raises(NotImplementedError):
             dve._read_ender(ender, config)
 
     rewarders = m.episode_rewarder
     steps = (rewarders.DeltaRewarder(1, 0.5) + rewarders.ObservationRewarder(1)
              + rewarders.OnTargetRewarder((0, 1), 0.25))
-    dve._read_rewarder(steps, config)
-    assert (config.rewarder, config.delta_reward, config.delta_scale) == (_lib.ENV_REWARD_STEPS, -1.0, 0.5)
-    assert (config.on_span, config.on_off, config.on_delta) == (0.25, 0.0, 1.0)
-    jumps = rewarders.ObservationRewarder(1) + rewarders.StoppedRewarder(1, 0.125) * rewarders.OnTargetRewarder(
-        (0, 1), 0.25)
-    dve._read_rewarder(jumps, config)
-    assert (config.rewarder, config.stop_threshold, config.stop_reward) == (_lib.ENV_REWARD_JUMPS, 0.125, 1.0)
-    for rewarder in (rewarders.DistanceRewarder((0, 1), 5.0), rewarders.ObservationRewarder(1),
-                     rewarders.DeltaRewarder(0, 0.5) + rewarders.ObservationRewarder(1)
-                     + rewarders.OnTargetRewarder((0, 1), 0.25),
-                     rewarders.DeltaRewarder(1, 0.5) + rewarders.ObservationRewarder(0)
-                     + rewarders.OnTargetRewarder((0, 1), 0.25)):
+    assert dve._read_rewarder(steps, config) is True  # bool * Python float makes it float64
+    kinds = [config.rewards[i].kind for i in range(config.n_rewards)]
+    assert kinds == [_lib.ENV_REWARD_DELTA, _lib.ENV_REWARD_OBSERVATION, _lib.ENV_REWARD_ADD,
+                     _lib.ENV_REWARD_ON_TARGET, _lib.ENV_REWARD_ADD]
+    assert (config.rewards[0].f0, config.rewards[0].f1) == (-1.0, 0.5)
+    assert (config.rewards[3].f0, config.rewards[3].d0, config.rewards[3].d1) == (0.25, 0.0, 1.0)
+    narrow = rewarders.DistanceRewarder((0, 1), 5.0, -2.0, 1.0) * rewarders.ObservationRewarder(3)
+    assert dve._read_rewarder(narrow, config) is False  # float32 all the way
+    assert (config.rewards[0].f0, config.rewards[0].f1, config.rewards[0].d0) == (5.0, 3.0, -2.0)
+    for rewarder in (rewarders.DeltaRewarder(2, 0.5), rewarders.ObservationRewarder(4),
+                     rewarders.OpRewarder(steps, steps, numpy.subtract)):
         with pytest.raises(NotImplementedError):
             dve._read_rewarder(rewarder, config)
 

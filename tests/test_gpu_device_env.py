@@ -44,6 +44,25 @@ def _strategies(num_envs, renderer, seed, frame_height, kind="steps", max_steps=
             num_envs, 1, ENDS, numpy.concatenate([-moves, [0], moves[::-1]]))
         rewarder = (episode_rewarder.DeltaRewarder(1, 0.5) + episode_rewarder.ObservationRewarder(1)
                     + episode_rewarder.OnTargetRewarder((0, 1), 0.25))
+    elif kind == "other":
+        # every ender kind and the remaining rewarders in one tree; the rewards stay float32
+        ender = (episode_ender.OnTargetEnder(num_envs, (0, 1), 0.4, early_end_steps=2)
+                 | episode_ender.StoppedEnder(num_envs, 1, 0.05, early_end_steps=3)) & (
+            episode_ender.EndlessEnder(num_envs) | episode_ender.TimeLimitEnder(num_envs, 3))
+        transformer = state_transformer.ContinuousMoveTransformer(num_envs, 1, ENDS, 2.0, 0.3)
+        rewarder = (episode_rewarder.DistanceRewarder((0, 1), 5.0, -2.0, 1.0)
+                    * episode_rewarder.ObservationRewarder(3) + episode_rewarder.DeltaRewarder(0, 0.25, 2.0))
+    elif kind == "mixed":
+        # float64 only through the product: Stopped * Distance, plus OnTarget with an offset
+        ender = episode_ender.StoppedEnder(num_envs, 1, 0.2, early_end_steps=2) | (
+            episode_ender.TimeLimitEnder(num_envs, 9)
+            & episode_ender.DivergingEnder(num_envs, (1, 0), 0.05, early_end_steps=1))
+        moves = 5.0 / 2.0 ** numpy.arange(6)
+        transformer = state_transformer.DiscreteMoveTransformer(
+            num_envs, 1, ENDS, numpy.concatenate([-moves, [0], moves[::-1]]))
+        rewarder = (episode_rewarder.StoppedRewarder(1, 0.2, 3.0)
+                    * episode_rewarder.DistanceRewarder((1, 0), 4.0, -1.0, 0.5)
+                    + episode_rewarder.OnTargetRewarder((0, 1), 1.0, 0.5, 2.0))
     elif kind in ("moves", "positions"):
         if kind == "moves":
             transformer = state_transformer.ContinuousMoveTransformer(num_envs, 1, ENDS, 2.5, 0.125)
@@ -165,6 +184,22 @@ def test_discrete_jump_device_env_equals_host_env(torch):
     host, device = _pair(6, seed=39, frame_height=48, spp=8, kind="positions")
     actions = numpy.random.Generator(numpy.random.PCG64(10)).integers(0, 9, (50, 6))
     assert _assert_same_rollout(host, device, actions) > 0
+
+
+@pytest.mark.parametrize("kind", ["other", "mixed"])
+def test_device_env_with_every_ender_and_rewarder_kind(torch, kind):
+    """Ender / rewarder trees beyond the example envs: OnTarget, Stopped and Endless enders
+    under & and |, Distance / Stopped rewarders under * and +, float32 and float64 results."""
+
+    host, device = _pair(7, seed=40, frame_height=40, spp=6, kind=kind)
+    rng = numpy.random.Generator(numpy.random.PCG64(11))
+    if kind == "other":
+        actions = rng.uniform(-1.2, 1.2, (70, 7, 1)).astype(numpy.float32)
+        actions[::3] *= 0.05
+    else:
+        actions = rng.integers(0, 13, (70, 7))
+        actions[::4] = 6  # the zero move: stopped episodes
+    assert _assert_same_rollout(host, device, actions) > 7
 
 
 def test_device_env_with_more_envs_than_one_scan_chunk(torch):
