@@ -258,7 +258,8 @@ int rf_env_reset(rf_env *env, float *d_obs, void *stream);
 /* step(): d_actions [n] of the given kind; d_obs float32 [n, 4], d_rewards float64 [n],
  * d_truncated uint8 [n] (nothing ever terminates, as in the reference); *h_resets, if not
  * NULL, receives the number of envs that restarted. The host waits only for that count,
- * which is known before the main render starts; the outputs are stream-ordered. */
+ * which is known before the main render starts; the outputs are stream-ordered. Drive an
+ * env from one stream: its state lives in device memory and is ordered only by that stream. */
 int rf_env_step(rf_env *env, const void *d_actions, int action_kind, float *d_obs,
                 double *d_rewards, uint8_t *d_truncated, int *h_resets, void *stream);
 /* Synchronous copies of the env's episode state to / from host memory (parity tests,
