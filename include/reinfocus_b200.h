@@ -196,8 +196,9 @@ int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float 
  *   ender        any tree of TimeLimitEnder, DivergingEnder, OnTargetEnder, StoppedEnder,
  *                EndlessEnder combined with & and | (episode_ender.py:112-656), given as a
  *                postfix program of rf_env_ender nodes
- *   observer     NormalizedObserver(DeltaObserver([IndexedElementObserver(plane),
- *                FocusObserver], include_original=True)) (state_observer.py:167-517)
+ *   observer     IndexedElementObservers and one FocusObserver side by side, optionally
+ *                under a DeltaObserver, optionally under a NormalizedObserver
+ *                (state_observer.py:103-517)
  *   rewarder     any tree of DeltaRewarder, DistanceRewarder, ObservationRewarder,
  *                OnTargetRewarder, StoppedRewarder combined with + and *
  *                (episode_rewarder.py:86-429), as a postfix program of rf_env_reward nodes;
@@ -244,7 +245,14 @@ typedef struct {
     int n_enders, n_rewards; /* program lengths, 1..8 each */
     rf_env_ender enders[8];
     rf_env_reward rewards[8];
-    float obs_mid[4], obs_scale[4]; /* NormalizedObserver._mid / ._scale */
+    /* observer: n_base (1..4) base observers side by side, base_index = the state element an
+     * IndexedElementObserver shows or -1 for the FocusObserver (exactly one); obs_delta: they
+     * sit under a DeltaObserver (obs_original: with include_original); obs_normalized: a
+     * NormalizedObserver on top, with its _mid / _scale per output column. The observation
+     * has n_base columns, times two for a DeltaObserver with include_original. */
+    int n_base, base_index[4];
+    int obs_delta, obs_original, obs_normalized;
+    float obs_mid[8], obs_scale[8];
     double init_low[2], init_high[2];
     rf_scene_packing packing;
 } rf_env_config;
@@ -253,9 +261,11 @@ int rf_env_destroy(rf_env *env);
 /* numpy.random.PCG64DXSM().state: 128-bit state and increment as (high, low) words. */
 int rf_env_set_generator(rf_env *env, const uint64_t state[2], const uint64_t inc[2]);
 int rf_env_get_generator(rf_env *env, uint64_t state[2], uint64_t inc[2]); /* synchronous */
-/* reset(): every env starts an episode; d_obs float32 [n, 4]. */
+/* Columns of an observation (rf_env_reset / rf_env_step write float32 [n, rf_env_obs_dim]). */
+int rf_env_obs_dim(const rf_env *env);
+/* reset(): every env starts an episode; d_obs float32 [n, obs_dim]. */
 int rf_env_reset(rf_env *env, float *d_obs, void *stream);
-/* step(): d_actions [n] of the given kind; d_obs float32 [n, 4], d_rewards float64 [n],
+/* step(): d_actions [n] of the given kind; d_obs float32 [n, obs_dim], d_rewards float64 [n],
  * d_truncated uint8 [n] (nothing ever terminates, as in the reference); *h_resets, if not
  * NULL, receives the number of envs that restarted. The host waits only for that count,
  * which is known before the main render starts; the outputs are stream-ordered. Drive an
@@ -266,7 +276,7 @@ int rf_env_step(rf_env *env, const void *d_actions, int action_kind, float *d_ob
  * checkpoint / resume; the reference cannot serialise an env). Together with the generator
  * (rf_env_get/set_generator) and the renderer's RNG states (rf_rng_export/import) this is
  * everything a resumed run needs to continue bit-identically. h_states float32 [n, 2],
- * h_old_obs float32 [n, 2] (DeltaObserver), h_node_state uint32 [rf_env_node_rows(env), n]
+ * h_old_obs float32 [n, 4] (DeltaObserver), h_node_state uint32 [rf_env_node_rows(env), n]
  * (the enders' counters / windows and the rewarders' previous values, raw bits). Export
  * skips NULL pointers; import needs all of them and stands in for a reset. */
 int rf_env_node_rows(const rf_env *env);

@@ -19,7 +19,7 @@ RF_ERR_CUDA = -2
 RF_ERR_NOMEM = -3
 RF_ERR_NO_SCENE = -4
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH, SELFTEST_CONST_DIV = 0, 1, 2, 3
 OPT_FORCE_GENERIC = 0
@@ -84,7 +84,9 @@ class EnvConfig(ctypes.Structure):
         ("n_enders", ctypes.c_int), ("n_rewards", ctypes.c_int),
         ("enders", EnvEnder * 8),
         ("rewards", EnvReward * 8),
-        ("obs_mid", ctypes.c_float * 4), ("obs_scale", ctypes.c_float * 4),
+        ("n_base", ctypes.c_int), ("base_index", ctypes.c_int * 4),
+        ("obs_delta", ctypes.c_int), ("obs_original", ctypes.c_int), ("obs_normalized", ctypes.c_int),
+        ("obs_mid", ctypes.c_float * 8), ("obs_scale", ctypes.c_float * 8),
         ("init_low", ctypes.c_double * 2), ("init_high", ctypes.c_double * 2),
         ("packing", ScenePacking),
     ]
@@ -135,6 +137,7 @@ _SIGNATURES = {
     "rf_env_step": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp, _vp,
                                    ctypes.POINTER(ctypes.c_int), _vp]),
     "rf_env_node_rows": (ctypes.c_int, [_vp]),
+    "rf_env_obs_dim": (ctypes.c_int, [_vp]),
     "rf_env_export": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "rf_env_import": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "rf_selftest": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int,
@@ -393,6 +396,7 @@ class DeviceEnv:
         context._check(  # pylint: disable=protected-access
             self._lib.rf_env_create(context._handle, ctypes.byref(config), ctypes.byref(handle)))
         self._handle = handle
+        self.obs_dim = int(self._lib.rf_env_obs_dim(handle))
 
     def close(self):
         if getattr(self, "_handle", None):
@@ -434,7 +438,7 @@ class DeviceEnv:
 
     def _layout(self):
         rows = int(self._lib.rf_env_node_rows(self._handle))
-        return (("states", numpy.float32, (self.num_envs, 2)), ("old_obs", numpy.float32, (self.num_envs, 2)),
+        return (("states", numpy.float32, (self.num_envs, 2)), ("old_obs", numpy.float32, (self.num_envs, 4)),
                 ("node_state", numpy.uint32, (rows, self.num_envs)))
 
     def export(self) -> dict:

@@ -18,7 +18,7 @@
 #include "rf_rng.cuh"
 #include "rf_tracer.cuh"
 
-#define RF_ABI_VERSION 6
+#define RF_ABI_VERSION 7
 
 namespace {
 
@@ -796,6 +796,28 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
     p.limit_hi = c->limits[1];
     p.jump_span = c->jump_span;
     p.jump_threshold = c->jump_threshold;
+    int focus_observers = 0;
+    bool observer_ok = c->n_base >= 1 && c->n_base <= rf::kEnvMaxBase;
+    for (int b = 0; observer_ok && b < c->n_base; ++b) {
+        observer_ok = c->base_index[b] >= -1 && c->base_index[b] <= 1;
+        focus_observers += c->base_index[b] < 0;
+        p.base_index[b] = c->base_index[b];
+    }
+    if (!observer_ok || focus_observers != 1) {
+        delete env;
+        return fail(ctx, RF_ERR_INVALID,
+                    "rf_env_create: the observer needs 1..%d base observers, exactly one of them the focus value",
+                    rf::kEnvMaxBase);
+    }
+    p.n_base = c->n_base;
+    p.obs_delta = c->obs_delta != 0;
+    p.obs_original = p.obs_delta && c->obs_original != 0;
+    p.obs_normalized = c->obs_normalized != 0;
+    p.obs_dim = p.n_base * (p.obs_original ? 2 : 1);
+    for (int i = 0; i < 2 * rf::kEnvMaxBase; ++i) {
+        p.obs_mid[i] = c->obs_mid[i];
+        p.obs_scale[i] = c->obs_scale[i];
+    }
     // the programs: check that they are well-formed postfix expressions over state indices
     // 0 / 1, and give every node its per-env state rows
     int rows = 0, depth = 0;
@@ -829,7 +851,7 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
         node = rf::RewardNode{src.kind, src.i0, src.i1, rows, src.f0, src.f1, src.d0, src.d1};
         const bool leaf = src.kind >= RF_ENV_REWARD_DELTA && src.kind <= RF_ENV_REWARD_STOPPED;
         const bool op = src.kind == RF_ENV_REWARD_ADD || src.kind == RF_ENV_REWARD_MUL;
-        const int max_index = src.kind == RF_ENV_REWARD_OBSERVATION ? 3 : 1;
+        const int max_index = src.kind == RF_ENV_REWARD_OBSERVATION ? p.obs_dim - 1 : 1;
         const bool indices_ok = src.i0 >= 0 && src.i0 <= max_index && src.i1 >= 0 && src.i1 <= 1;
         if (!(leaf || op) || !indices_ok || (op && depth < 2)) {
             delete env;
@@ -843,10 +865,6 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
         return fail(ctx, RF_ERR_INVALID, "rf_env_create: the rewarder program does not reduce to one value");
     }
     env->node_rows = std::max(rows, 1);
-    for (int i = 0; i < 4; ++i) {
-        p.obs_mid[i] = c->obs_mid[i];
-        p.obs_scale[i] = c->obs_scale[i];
-    }
     for (int i = 0; i < 2; ++i) {
         p.init_low[i] = c->init_low[i];
         p.init_range[i] = c->init_high[i] - c->init_low[i];  // Generator.uniform: high - low in float64
@@ -860,7 +878,7 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
     const bool ok = alloc((void **)&a.states, sizeof(float) * 2 * n) &&
                     alloc((void **)&a.new_states, sizeof(float) * 2 * n) &&
                     alloc((void **)&a.reset_rank, sizeof(int) * n) &&
-                    alloc((void **)&a.old_obs, sizeof(float) * 2 * n) &&
+                    alloc((void **)&a.old_obs, sizeof(float) * rf::kEnvMaxBase * n) &&
                     alloc((void **)&a.node_state, sizeof(uint32_t) * n * (size_t)env->node_rows) &&
                     alloc((void **)&a.generator, sizeof(uint64_t) * 4) &&
                     alloc((void **)&a.counters, sizeof(int) * 2) &&
@@ -998,7 +1016,7 @@ int env_copy_arrays(rf_env *env, bool to_host, float *h_states, float *h_old_obs
         size_t bytes;
     } items[] = {
         {h_states, a.states, sizeof(float) * 2 * n},
-        {h_old_obs, a.old_obs, sizeof(float) * 2 * n},
+        {h_old_obs, a.old_obs, sizeof(float) * rf::kEnvMaxBase * n},
         {h_node_state, a.node_state, sizeof(uint32_t) * n * (size_t)env->node_rows},
     };
     for (const Item &item : items) {
@@ -1014,6 +1032,8 @@ int env_copy_arrays(rf_env *env, bool to_host, float *h_states, float *h_old_obs
 }  // namespace
 
 int rf_env_node_rows(const rf_env *env) { return env ? env->node_rows : 0; }
+
+int rf_env_obs_dim(const rf_env *env) { return env ? env->params.obs_dim : 0; }
 
 int rf_env_export(rf_env *env, float *h_states, float *h_old_obs, uint32_t *h_node_state) {
     if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_export: env is NULL");

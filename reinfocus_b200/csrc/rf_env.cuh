@@ -23,6 +23,7 @@ enum { kRewardDelta = 0, kRewardDistance = 1, kRewardObservation = 2, kRewardOnT
        kRewardAdd = 5, kRewardMul = 6 };
 constexpr int kEnvMaxMoves = 32;
 constexpr int kEnvMaxNodes = 8;
+constexpr int kEnvMaxBase = 4;
 constexpr int kEnvMaxWindow = 16;  // StoppedEnder: early_end_steps + 1 positions
 constexpr int kEnvPreThreads = 1024;
 
@@ -55,7 +56,12 @@ struct EnvParams {
     int n_enders, n_rewards;
     EnderNode enders[kEnvMaxNodes];
     RewardNode rewards[kEnvMaxNodes];
-    float obs_mid[4], obs_scale[4];     // NormalizedObserver
+    // observer: n_base base observers side by side (a state element, or the focus value for
+    // index -1), optionally under a DeltaObserver (changes, preceded by the values themselves
+    // with include_original), optionally under a NormalizedObserver
+    int n_base, base_index[kEnvMaxBase];
+    int obs_delta, obs_original, obs_normalized, obs_dim;
+    float obs_mid[2 * kEnvMaxBase], obs_scale[2 * kEnvMaxBase];  // NormalizedObserver
     double init_low[2], init_range[2];  // RangedInitializer, one range per element
 };
 
@@ -63,7 +69,7 @@ struct EnvArrays {
     float *states;        // [n, 2]  target, focus plane
     float *new_states;    // [n, 2]  first states of restarted episodes, by reset rank
     int *reset_rank;      // [n]     position among this step's restarted envs, -1 if none
-    float *old_obs;       // [n, 2]  DeltaObserver: previous [focus plane, focus value]
+    float *old_obs;       // [n, kEnvMaxBase]  DeltaObserver: the base observers' previous values
     uint32_t *node_state; // [rows, n] per-env state of the ender / rewarder nodes (int or float bits)
     uint64_t *generator;  // [4]     PCG64DXSM state hi, lo, increment hi, lo
     int *counters;        // [2]     number of restarted envs, invalid-action flag
@@ -113,9 +119,30 @@ __device__ inline float clip_f32(float x, float lo, float hi) {
 
 __device__ inline float env_gap(float target, float plane) { return fabsf(__fsub_rn(target, plane)); }
 
-__device__ inline float normalized(const EnvParams &p, int column, float value) {
-    // NormalizedObserver._normalize: clip((values - mid) / scale, -1, 1)
-    return clip_f32(__fdiv_rn(__fsub_rn(value, p.obs_mid[column]), p.obs_scale[column]), -1.0f, 1.0f);
+// observer.observe / observer.reset of one env: the wrapped observers' values side by side
+// (hstack casts the float64 focus value to float32), DeltaObserver's changes since the
+// previous step (zeros when the episode just started, reference state_observer.py:283-290),
+// NormalizedObserver's clip((values - mid) / scale, -1, 1)
+__device__ inline void observe(const EnvParams &p, const EnvArrays &a, int env, const float *state, double focus,
+                               bool fresh, float *out) {
+    float current[kEnvMaxBase];
+    for (int b = 0; b < p.n_base; ++b)
+        current[b] = p.base_index[b] < 0 ? __double2float_rn(focus) : state[p.base_index[b]];
+    int dim = 0;
+    if (!p.obs_delta) {
+        for (int b = 0; b < p.n_base; ++b) out[dim++] = current[b];
+    } else {
+        if (p.obs_original)
+            for (int b = 0; b < p.n_base; ++b) out[dim++] = current[b];
+        for (int b = 0; b < p.n_base; ++b) {
+            float &previous = a.old_obs[(size_t)kEnvMaxBase * env + b];
+            out[dim++] = fresh ? 0.0f : __fsub_rn(current[b], previous);
+            previous = current[b];
+        }
+    }
+    if (p.obs_normalized)
+        for (int c = 0; c < dim; ++c)
+            out[c] = clip_f32(__fdiv_rn(__fsub_rn(out[c], p.obs_mid[c]), p.obs_scale[c]), -1.0f, 1.0f);
 }
 
 // per-env state rows of the strategy nodes
@@ -395,42 +422,23 @@ __global__ void env_post_kernel(EnvParams p, EnvArrays a, const double *focus_ma
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
     const int rank = a.reset_rank[i];
-    float out[4];
+    float out[2 * kEnvMaxBase];
     if (!reset_all) {
-        const float target = a.states[2 * i], plane = a.states[2 * i + 1];
-        // DeltaObserver over [IndexedElementObserver(plane), FocusObserver]; hstack casts the
-        // float64 focus value to float32
-        const float value = __double2float_rn(focus_main[i]);
-        const float raw[4] = {plane, value, __fsub_rn(plane, a.old_obs[2 * i]),
-                              __fsub_rn(value, a.old_obs[2 * i + 1])};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) out[c] = normalized(p, c, raw[c]);
-        a.old_obs[2 * i] = plane;
-        a.old_obs[2 * i + 1] = value;
-
-        const float state[2] = {target, plane};
-        const double reward = rewards_eval(p, a, i, state, out).value;
-        rewards[i] = reward;
+        const float state[2] = {a.states[2 * i], a.states[2 * i + 1]};
+        observe(p, a, i, state, focus_main[i], false, out);
+        rewards[i] = rewards_eval(p, a, i, state, out).value;
         truncated[i] = rank >= 0;
     }
     if (rank >= 0) {
         // same-step auto-reset (reference vector_environment.py:137-151)
-        const float target = a.new_states[2 * rank], plane = a.new_states[2 * rank + 1];
-        a.states[2 * i] = target;
-        a.states[2 * i + 1] = plane;
-        const float state[2] = {target, plane};
+        const float state[2] = {a.new_states[2 * rank], a.new_states[2 * rank + 1]};
+        a.states[2 * i] = state[0];
+        a.states[2 * i + 1] = state[1];
         enders_reset(p, a, i, state);
+        observe(p, a, i, state, focus_reset[rank], true, out);
         rewards_reset(p, a, i, state);
-        const float value = __double2float_rn(focus_reset[rank]);
-        a.old_obs[2 * i] = plane;
-        a.old_obs[2 * i + 1] = value;
-        out[0] = normalized(p, 0, plane);
-        out[1] = normalized(p, 1, value);
-        out[2] = normalized(p, 2, 0.0f);  // DeltaObserver emits zero changes on reset
-        out[3] = normalized(p, 3, 0.0f);
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) obs[4 * i + c] = out[c];
+    for (int c = 0; c < p.obs_dim; ++c) obs[(size_t)p.obs_dim * i + c] = out[c];
 }
 
 // ------------------------------------------------------------------- scene packing (a1, a2)

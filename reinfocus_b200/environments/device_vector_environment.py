@@ -14,8 +14,8 @@ What is understood (anything else raises ``NotImplementedError`` - use ``VectorE
 * any of the four transformers (discrete / continuous, move / jump) on the focus plane;
 * any ``&`` / ``|`` tree of ``TimeLimitEnder``, ``DivergingEnder``, ``OnTargetEnder``,
   ``StoppedEnder``, ``EndlessEnder`` (up to 8 nodes);
-* observer ``NormalizedObserver(DeltaObserver([IndexedElementObserver(focus plane),
-  FocusObserver], include_original=True, ...))``;
+* observer: ``IndexedElementObserver``s and one ``FocusObserver`` side by side, optionally under
+  a ``DeltaObserver``, optionally under a ``NormalizedObserver``;
 * any ``+`` / ``*`` tree of ``DeltaRewarder``, ``DistanceRewarder``, ``ObservationRewarder``,
   ``OnTargetRewarder``, ``StoppedRewarder`` (up to 8 nodes), with NumPy's result types;
 * initializer ``RangedInitializer`` with one range per element and a PCG64DXSM generator.
@@ -127,7 +127,7 @@ def _read_ender(ender, config: _lib.EnvConfig):
         config.enders[i] = node
 
 
-def _read_rewarder(rewarder, config: _lib.EnvConfig) -> bool:
+def _read_rewarder(rewarder, config: _lib.EnvConfig, columns: int = 4) -> bool:
     """Flattens the rewarder tree into the postfix program of rf_env_config. Returns whether
     NumPy would make the rewards float64 (a float32 tree stays float32)."""
 
@@ -154,7 +154,7 @@ def _read_rewarder(rewarder, config: _lib.EnvConfig) -> bool:
             return False
         if isinstance(node, episode_rewarder.ObservationRewarder):
             column = int(node._reward_observation_index)
-            if not 0 <= column < 4:
+            if not 0 <= column < columns:
                 _unsupported("rewarder (observation column out of range)")
             program.append(_lib.EnvReward(_lib.ENV_REWARD_OBSERVATION, column, 0, 0.0, 0.0, 0.0, 0.0))
             return False
@@ -180,25 +180,46 @@ def _read_rewarder(rewarder, config: _lib.EnvConfig) -> bool:
 
 
 def _read_observer(observer, config: _lib.EnvConfig):
+    """IndexedElementObservers and exactly one FocusObserver side by side, optionally under a
+    DeltaObserver, optionally under a NormalizedObserver. Returns the FocusObserver's renderer."""
+
     # pylint: disable=protected-access
-    if not (isinstance(observer, state_observer.NormalizedObserver) and len(observer._observers) == 1):
+    def is_base(node):
+        return isinstance(node, (state_observer.IndexedElementObserver, state_observer.FocusObserver))
+
+    normalized = isinstance(observer, state_observer.NormalizedObserver)
+    inner = list(observer._observers) if normalized else [observer]
+    delta = None
+    if len(inner) == 1 and isinstance(inner[0], state_observer.DeltaObserver):
+        delta = inner[0]
+        bases = list(delta._observers)
+    elif normalized:
+        bases = inner
+    else:
         _unsupported("observer")
-    delta = observer._observers[0]
-    if not (isinstance(delta, state_observer.DeltaObserver) and delta._include_original
-            and len(delta._observers) == 2):
+    if not bases or len(bases) > 4 or not all(is_base(base) for base in bases):
         _unsupported("observer")
-    plane, focus = delta._observers
-    if not (isinstance(plane, state_observer.IndexedElementObserver)
-            and plane._element_index == FOCUS_PLANE
-            and isinstance(focus, state_observer.FocusObserver)
-            and focus._target_index == TARGET and focus._focus_plane_index == FOCUS_PLANE):
-        _unsupported("observer")
-    assert observer._mid.dtype == numpy.float32 and observer._scale.dtype == numpy.float32
-    for i in range(4):
-        config.obs_mid[i] = float(observer._mid[i])
-        config.obs_scale[i] = float(observer._scale[i])
+    focus_observers = [base for base in bases if isinstance(base, state_observer.FocusObserver)]
+    if len(focus_observers) != 1:
+        _unsupported("observer (exactly one FocusObserver renders per step)")
+    focus = focus_observers[0]
+    if (focus._target_index, focus._focus_plane_index) != (TARGET, FOCUS_PLANE):
+        _unsupported("observer (the FocusObserver must read [target, focus plane])")
+    config.n_base = len(bases)
+    for i, base in enumerate(bases):
+        config.base_index[i] = -1 if base is focus else _state_index(base._element_index)
+    config.obs_delta = int(delta is not None)
+    config.obs_original = int(delta is not None and delta._include_original)
+    config.obs_normalized = int(normalized)
+    columns = len(bases) * (2 if config.obs_original else 1)
+    if normalized:
+        assert observer._mid.dtype == numpy.float32 and observer._scale.dtype == numpy.float32
+        assert len(observer._mid) == columns
+        for i in range(columns):
+            config.obs_mid[i] = float(observer._mid[i])
+            config.obs_scale[i] = float(observer._scale[i])
     config.frame_height = int(focus._frame_height)
-    return focus._renderer
+    return focus._renderer, columns
 
 
 def _read_initializer(initializer, config: _lib.EnvConfig):
@@ -218,7 +239,7 @@ def _read_initializer(initializer, config: _lib.EnvConfig):
 class DeviceVectorEnvironment(gym_compat.VectorEnv):
     # pylint: disable=too-many-instance-attributes
     """``VectorEnvironment`` with the step on the GPU. ``reset`` / ``step`` return torch CUDA
-    tensors: observations float32 (n, 4), rewards float64 (n,), terminated / truncated bool
+    tensors: observations float32 (n, columns), rewards float64 or float32 (n,), terminated / truncated bool
     (n,). ``step`` takes actions as a torch CUDA tensor (int32 / int64 for discrete moves,
     float32 for jumps) or anything ``numpy.asarray`` understands (copied to the GPU).
 
@@ -243,8 +264,8 @@ class DeviceVectorEnvironment(gym_compat.VectorEnv):
         config.num_envs = num_envs
         _read_transformer(transformer, config)
         _read_ender(ender, config)
-        self._wide_rewards = _read_rewarder(rewarder, config)
-        renderer = _read_observer(observer, config)
+        renderer, self._columns = _read_observer(observer, config)
+        self._wide_rewards = _read_rewarder(rewarder, config, self._columns)
         generator = _read_initializer(initializer, config)
         config.samples_per_pixel = renderer.samples_per_pixel
         config.packing = renderer.scene_packing()
@@ -263,7 +284,7 @@ class DeviceVectorEnvironment(gym_compat.VectorEnv):
         import torch
 
         super().reset(seed=seed)
-        observations = torch.empty((self.num_envs, 4), dtype=torch.float32, device=self._device)
+        observations = torch.empty((self.num_envs, self._columns), dtype=torch.float32, device=self._device)
         self._renderer.scene_overwritten()
         self._env.reset(observations.data_ptr())
         self._started = True
@@ -274,7 +295,7 @@ class DeviceVectorEnvironment(gym_compat.VectorEnv):
 
         assert self._started, "reset the env first"
         actions, kind = self._device_actions(actions)
-        observations = torch.empty((self.num_envs, 4), dtype=torch.float32, device=self._device)
+        observations = torch.empty((self.num_envs, self._columns), dtype=torch.float32, device=self._device)
         rewards = torch.empty((self.num_envs,), dtype=torch.float64, device=self._device)
         truncated = torch.empty((self.num_envs,), dtype=torch.bool, device=self._device)
         terminated = torch.zeros((self.num_envs,), dtype=torch.bool, device=self._device)

@@ -27,14 +27,20 @@ def _generator(seed):
     return numpy.random.Generator(numpy.random.PCG64DXSM(seed))
 
 
-def _strategies(num_envs, renderer, seed, frame_height, kind="steps", max_steps=20):
+def _strategies(num_envs, renderer, seed, frame_height, kind="steps", max_steps=20, observer_kind="example"):
     from reinfocus_b200.environments import (episode_ender, episode_rewarder, state_initializer,
                                              state_observer, state_transformer)
 
-    observer = state_observer.NormalizedObserver(state_observer.DeltaObserver(
-        [state_observer.IndexedElementObserver(num_envs, 1, *ENDS),
-         state_observer.FocusObserver(num_envs, 0, 1, ENDS, renderer, frame_height)],
-        True, numpy.array([5.0, numpy.nan])))
+    focus = state_observer.FocusObserver(num_envs, 0, 1, ENDS, renderer, frame_height)
+    plane = state_observer.IndexedElementObserver(num_envs, 1, *ENDS)
+    target = state_observer.IndexedElementObserver(num_envs, 0, *ENDS)
+    if observer_kind == "example":
+        observer = state_observer.NormalizedObserver(state_observer.DeltaObserver(
+            [plane, focus], True, numpy.array([5.0, numpy.nan])))
+    elif observer_kind == "changes":  # three raw changes, neither the values nor a normalisation
+        observer = state_observer.DeltaObserver([target, focus, plane])
+    else:  # "levels": normalised values without a DeltaObserver
+        observer = state_observer.NormalizedObserver([focus, plane])
     ender = episode_ender.DivergingEnder(num_envs, (0, 1), 0.125, early_end_steps=3)
     if max_steps:
         ender = episode_ender.TimeLimitEnder(num_envs, max_steps) | ender
@@ -97,6 +103,18 @@ def _pair(num_envs, seed, frame_height=300, spp=100, **kwargs):
     return host, device
 
 
+def _host_renderer(observer):
+    """The renderer of the FocusObserver somewhere below ``observer``."""
+
+    if hasattr(observer, "_renderer"):
+        return observer._renderer
+    for child in getattr(observer, "_observers", []):
+        found = _host_renderer(child)
+        if found is not None:
+            return found
+    return None
+
+
 def _assert_same_rollout(host, device, actions):
     want_obs, _ = host.reset()
     got_obs, _ = device.reset()
@@ -117,7 +135,7 @@ def _assert_same_rollout(host, device, actions):
     host_generator = host._initializer._generator.bit_generator.state["state"]
     assert device.generator_state() == (host_generator["state"], host_generator["inc"])
     numpy.testing.assert_array_equal(device._renderer.context.rng_export(0, 4096),
-                                     host._observer._observers[0]._observers[1]._renderer.context.rng_export(0, 4096))
+                                     _host_renderer(host._observer).context.rng_export(0, 4096))
     return resets
 
 
@@ -184,6 +202,30 @@ def test_discrete_jump_device_env_equals_host_env(torch):
     host, device = _pair(6, seed=39, frame_height=48, spp=8, kind="positions")
     actions = numpy.random.Generator(numpy.random.PCG64(10)).integers(0, 9, (50, 6))
     assert _assert_same_rollout(host, device, actions) > 0
+
+
+@pytest.mark.parametrize("observer_kind,reward_column", [("changes", 1), ("levels", 0)])
+def test_device_env_with_other_observer_layouts(torch, observer_kind, reward_column):
+    """Observer layouts beyond the example envs': a bare DeltaObserver over three base
+    observers (changes only, not normalised) and a NormalizedObserver without a DeltaObserver;
+    the ObservationRewarder reads the focus column of each."""
+
+    from reinfocus_b200.environments import device_vector_environment, episode_rewarder, vector_environment
+    from reinfocus_b200.graphics import render
+
+    def build(env_class, **extra):
+        parts = _strategies(6, render.FastRenderer(samples_per_pixel=6), 41, 40, observer_kind=observer_kind)
+        parts["rewarder"] = (episode_rewarder.ObservationRewarder(reward_column)
+                             + episode_rewarder.OnTargetRewarder((0, 1), 0.25))
+        return env_class(**parts, num_envs=6, **extra)
+
+    host = build(vector_environment.VectorEnvironment, visualizer=None)
+    device = build(device_vector_environment.DeviceVectorEnvironment)
+    assert device.reset()[0].shape == (6, 3 if observer_kind == "changes" else 2)
+    host, device = (build(vector_environment.VectorEnvironment, visualizer=None),
+                    build(device_vector_environment.DeviceVectorEnvironment))
+    actions = numpy.random.Generator(numpy.random.PCG64(12)).integers(0, 13, (50, 6))
+    assert _assert_same_rollout(host, device, actions) > 6
 
 
 @pytest.mark.parametrize("kind", ["other", "mixed"])
