@@ -203,7 +203,7 @@ int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float 
  *                OnTargetRewarder, StoppedRewarder combined with + and *
  *                (episode_rewarder.py:86-429), as a postfix program of rf_env_reward nodes;
  *                NumPy's result types are followed (float32 until a float64 operand joins)
- *   initializer  RangedInitializer, one range per element, numpy PCG64DXSM generator
+ *   initializer  RangedInitializer (up to 4 ranges per element), numpy PCG64DXSM generator
  *                (state_initializer.py:30-71)
  * States, observations, rewards and the generator live on the GPU; a step is two small
  * kernels around the render + focus launches of the context (and of the k restarted envs,
@@ -253,14 +253,20 @@ typedef struct {
     int n_base, base_index[4];
     int obs_delta, obs_original, obs_normalized;
     float obs_mid[8], obs_scale[8];
-    double init_low[2], init_high[2];
+    /* RangedInitializer: per state element 1..4 (low, high) ranges; with several, the range
+     * is picked like Generator.choice does before Generator.uniform draws inside it */
+    int init_options[2];
+    double init_low[2][4], init_high[2][4];
     rf_scene_packing packing;
 } rf_env_config;
 int rf_env_create(rf_ctx *ctx, const rf_env_config *config, rf_env **out);
 int rf_env_destroy(rf_env *env);
-/* numpy.random.PCG64DXSM().state: 128-bit state and increment as (high, low) words. */
-int rf_env_set_generator(rf_env *env, const uint64_t state[2], const uint64_t inc[2]);
-int rf_env_get_generator(rf_env *env, uint64_t state[2], uint64_t inc[2]); /* synchronous */
+/* numpy.random.PCG64DXSM().state: 128-bit state and increment as (high, low) words, plus
+ * the buffered 32-bit half (has_uint32, uinteger) that Generator.choice draws from. */
+int rf_env_set_generator(rf_env *env, const uint64_t state[2], const uint64_t inc[2], uint32_t has_uint32,
+                         uint32_t uinteger);
+int rf_env_get_generator(rf_env *env, uint64_t state[2], uint64_t inc[2], uint32_t *has_uint32,
+                         uint32_t *uinteger); /* synchronous */
 /* Columns of an observation (rf_env_reset / rf_env_step write float32 [n, rf_env_obs_dim]). */
 int rf_env_obs_dim(const rf_env *env);
 /* reset(): every env starts an episode; d_obs float32 [n, obs_dim]. */

@@ -19,7 +19,7 @@ RF_ERR_CUDA = -2
 RF_ERR_NOMEM = -3
 RF_ERR_NO_SCENE = -4
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH, SELFTEST_CONST_DIV = 0, 1, 2, 3
 OPT_FORCE_GENERIC = 0
@@ -87,7 +87,8 @@ class EnvConfig(ctypes.Structure):
         ("n_base", ctypes.c_int), ("base_index", ctypes.c_int * 4),
         ("obs_delta", ctypes.c_int), ("obs_original", ctypes.c_int), ("obs_normalized", ctypes.c_int),
         ("obs_mid", ctypes.c_float * 8), ("obs_scale", ctypes.c_float * 8),
-        ("init_low", ctypes.c_double * 2), ("init_high", ctypes.c_double * 2),
+        ("init_options", ctypes.c_int * 2),
+        ("init_low", (ctypes.c_double * 4) * 2), ("init_high", (ctypes.c_double * 4) * 2),
         ("packing", ScenePacking),
     ]
 
@@ -130,9 +131,10 @@ _SIGNATURES = {
     "rf_env_create": (ctypes.c_int, [_vp, ctypes.POINTER(EnvConfig), ctypes.POINTER(_vp)]),
     "rf_env_destroy": (ctypes.c_int, [_vp]),
     "rf_env_set_generator": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64),
-                                            ctypes.POINTER(ctypes.c_uint64)]),
+                                            ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint32, ctypes.c_uint32]),
     "rf_env_get_generator": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64),
-                                            ctypes.POINTER(ctypes.c_uint64)]),
+                                            ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32),
+                                            ctypes.POINTER(ctypes.c_uint32)]),
     "rf_env_reset": (ctypes.c_int, [_vp, _vp, _vp]),
     "rf_env_step": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp, _vp,
                                    ctypes.POINTER(ctypes.c_int), _vp]),
@@ -412,17 +414,21 @@ class DeviceEnv:
     def _check(self, rc: int):
         self._context._check(rc)  # pylint: disable=protected-access
 
-    def set_generator(self, state: int, inc: int):
-        """128-bit PCG64DXSM state and increment (numpy bit_generator.state['state'])."""
+    def set_generator(self, state: int, inc: int, has_uint32: int = 0, uinteger: int = 0):
+        """numpy ``bit_generator.state`` of a PCG64DXSM: 128-bit state and increment, and the
+        buffered 32-bit half."""
 
         pair = ctypes.c_uint64 * 2
         self._check(self._lib.rf_env_set_generator(
-            self._handle, pair(state >> 64, state & self._MASK64), pair(inc >> 64, inc & self._MASK64)))
+            self._handle, pair(state >> 64, state & self._MASK64), pair(inc >> 64, inc & self._MASK64),
+            int(has_uint32), int(uinteger)))
 
-    def get_generator(self) -> tuple[int, int]:
+    def get_generator(self) -> tuple[int, int, int, int]:
         state, inc = (ctypes.c_uint64 * 2)(), (ctypes.c_uint64 * 2)()
-        self._check(self._lib.rf_env_get_generator(self._handle, state, inc))
-        return (state[0] << 64) | state[1], (inc[0] << 64) | inc[1]
+        has_uint32, uinteger = ctypes.c_uint32(), ctypes.c_uint32()
+        self._check(self._lib.rf_env_get_generator(self._handle, state, inc, ctypes.byref(has_uint32),
+                                                   ctypes.byref(uinteger)))
+        return (state[0] << 64) | state[1], (inc[0] << 64) | inc[1], has_uint32.value, uinteger.value
 
     def reset(self, d_obs: int, stream=None):
         self._check(self._lib.rf_env_reset(self._handle, _vp(d_obs),

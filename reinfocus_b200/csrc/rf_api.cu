@@ -18,7 +18,7 @@
 #include "rf_rng.cuh"
 #include "rf_tracer.cuh"
 
-#define RF_ABI_VERSION 7
+#define RF_ABI_VERSION 8
 
 namespace {
 
@@ -866,8 +866,16 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
     }
     env->node_rows = std::max(rows, 1);
     for (int i = 0; i < 2; ++i) {
-        p.init_low[i] = c->init_low[i];
-        p.init_range[i] = c->init_high[i] - c->init_low[i];  // Generator.uniform: high - low in float64
+        if (c->init_options[i] < 1 || c->init_options[i] > rf::kEnvMaxRanges) {
+            delete env;
+            return fail(ctx, RF_ERR_INVALID, "rf_env_create: an initializer element has 1..%d ranges",
+                        rf::kEnvMaxRanges);
+        }
+        p.init_options[i] = c->init_options[i];
+        for (int k = 0; k < rf::kEnvMaxRanges; ++k) {
+            p.init_low[i][k] = c->init_low[i][k];
+            p.init_range[i][k] = c->init_high[i][k] - c->init_low[i][k];  // Generator.uniform: high - low in float64
+        }
     }
     const size_t n = (size_t)p.n;
     rf::EnvArrays &a = env->arrays;
@@ -880,7 +888,7 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
                     alloc((void **)&a.reset_rank, sizeof(int) * n) &&
                     alloc((void **)&a.old_obs, sizeof(float) * rf::kEnvMaxBase * n) &&
                     alloc((void **)&a.node_state, sizeof(uint32_t) * n * (size_t)env->node_rows) &&
-                    alloc((void **)&a.generator, sizeof(uint64_t) * 4) &&
+                    alloc((void **)&a.generator, sizeof(uint64_t) * 6) &&
                     alloc((void **)&a.counters, sizeof(int) * 2) &&
                     alloc((void **)&env->d_focus_main, sizeof(double) * n) &&
                     alloc((void **)&env->d_focus_reset, sizeof(double) * n) &&
@@ -896,30 +904,34 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
     return RF_OK;
 }
 
-int rf_env_set_generator(rf_env *env, const uint64_t state[2], const uint64_t inc[2]) {
+int rf_env_set_generator(rf_env *env, const uint64_t state[2], const uint64_t inc[2], uint32_t has_uint32,
+                         uint32_t uinteger) {
     if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_set_generator: env is NULL");
     rf_ctx *ctx = env->ctx;
     RF_REQUIRE(ctx, state && inc, "rf_env_set_generator: NULL argument");
     DeviceGuard guard(ctx->device);
-    const uint64_t words[4] = {state[0], state[1], inc[0], inc[1]};
+    const uint64_t words[6] = {state[0], state[1], inc[0], inc[1], has_uint32 ? 1u : 0u, uinteger};
     RF_CUDA(ctx, cudaDeviceSynchronize());
     RF_CUDA(ctx, cudaMemcpy(env->arrays.generator, words, sizeof(words), cudaMemcpyHostToDevice));
     env->seeded = true;
     return RF_OK;
 }
 
-int rf_env_get_generator(rf_env *env, uint64_t state[2], uint64_t inc[2]) {
+int rf_env_get_generator(rf_env *env, uint64_t state[2], uint64_t inc[2], uint32_t *has_uint32,
+                         uint32_t *uinteger) {
     if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_get_generator: env is NULL");
     rf_ctx *ctx = env->ctx;
-    RF_REQUIRE(ctx, state && inc, "rf_env_get_generator: NULL argument");
+    RF_REQUIRE(ctx, state && inc && has_uint32 && uinteger, "rf_env_get_generator: NULL argument");
     DeviceGuard guard(ctx->device);
-    uint64_t words[4];
+    uint64_t words[6];
     RF_CUDA(ctx, cudaDeviceSynchronize());
     RF_CUDA(ctx, cudaMemcpy(words, env->arrays.generator, sizeof(words), cudaMemcpyDeviceToHost));
     state[0] = words[0];
     state[1] = words[1];
     inc[0] = words[2];
     inc[1] = words[3];
+    *has_uint32 = (uint32_t)words[4];
+    *uinteger = (uint32_t)words[5];
     return RF_OK;
 }
 

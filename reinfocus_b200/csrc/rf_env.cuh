@@ -24,6 +24,7 @@ enum { kRewardDelta = 0, kRewardDistance = 1, kRewardObservation = 2, kRewardOnT
 constexpr int kEnvMaxMoves = 32;
 constexpr int kEnvMaxNodes = 8;
 constexpr int kEnvMaxBase = 4;
+constexpr int kEnvMaxRanges = 4;
 constexpr int kEnvMaxWindow = 16;  // StoppedEnder: early_end_steps + 1 positions
 constexpr int kEnvPreThreads = 1024;
 
@@ -62,7 +63,10 @@ struct EnvParams {
     int n_base, base_index[kEnvMaxBase];
     int obs_delta, obs_original, obs_normalized, obs_dim;
     float obs_mid[2 * kEnvMaxBase], obs_scale[2 * kEnvMaxBase];  // NormalizedObserver
-    double init_low[2], init_range[2];  // RangedInitializer, one range per element
+    // RangedInitializer: per state element up to kEnvMaxRanges (low, high - low) pairs; with
+    // more than one, Generator.choice picks the pair before Generator.uniform draws in it
+    int init_options[2];
+    double init_low[2][kEnvMaxRanges], init_range[2][kEnvMaxRanges];
 };
 
 struct EnvArrays {
@@ -71,7 +75,7 @@ struct EnvArrays {
     int *reset_rank;      // [n]     position among this step's restarted envs, -1 if none
     float *old_obs;       // [n, kEnvMaxBase]  DeltaObserver: the base observers' previous values
     uint32_t *node_state; // [rows, n] per-env state of the ender / rewarder nodes (int or float bits)
-    uint64_t *generator;  // [4]     PCG64DXSM state hi, lo, increment hi, lo
+    uint64_t *generator;  // [6]     PCG64DXSM state hi, lo, increment hi, lo, has_uint32, uinteger
     int *counters;        // [2]     number of restarted envs, invalid-action flag
 };
 
@@ -107,6 +111,51 @@ __device__ inline double pcg_next_double(u128 &state, u128 inc) {
     hi *= lo;
     state = state * kPcgCheapMultiplier + inc;
     return __dmul_rn((double)(hi >> 11), 1.0 / 9007199254740992.0);
+}
+
+__device__ inline uint64_t pcg_next64(u128 &state, u128 inc) {
+    uint64_t hi = (uint64_t)(state >> 64);
+    const uint64_t lo = (uint64_t)state | 1;
+    hi ^= hi >> 32;
+    hi *= kPcgCheapMultiplier;
+    hi ^= hi >> 48;
+    hi *= lo;
+    state = state * kPcgCheapMultiplier + inc;
+    return hi;
+}
+
+// numpy's buffered 32-bit draw (pcg64_cm_next32): the low half of a fresh 64-bit draw, then
+// its high half
+struct PcgBuffer {
+    uint32_t has, value;
+};
+__device__ inline uint32_t pcg_next32(u128 &state, u128 inc, PcgBuffer &buffer) {
+    if (buffer.has) {
+        buffer.has = 0;
+        return buffer.value;
+    }
+    const uint64_t v = pcg_next64(state, inc);
+    buffer.has = 1;
+    buffer.value = (uint32_t)(v >> 32);
+    return (uint32_t)v;
+}
+
+// Generator.integers(0, n) as Generator.choice uses it: Lemire's bounded draw on 32 bits
+// (numpy/random/src/distributions/distributions.c buffered_bounded_lemire_uint32); n = 1
+// consumes nothing
+__device__ inline uint32_t pcg_choice(u128 &state, u128 inc, PcgBuffer &buffer, uint32_t n) {
+    if (n <= 1) return 0;
+    const uint32_t rng = n - 1, exclusive = n;
+    uint64_t m = (uint64_t)pcg_next32(state, inc, buffer) * exclusive;
+    uint32_t leftover = (uint32_t)m;
+    if (leftover < exclusive) {
+        const uint32_t threshold = (0xffffffffu - rng) % exclusive;
+        while (leftover < threshold) {
+            m = (uint64_t)pcg_next32(state, inc, buffer) * exclusive;
+            leftover = (uint32_t)m;
+        }
+    }
+    return (uint32_t)(m >> 32);
 }
 
 // ------------------------------------------------------------------------------- helpers
@@ -314,6 +363,9 @@ env_pre_kernel(EnvParams p, EnvArrays a, const void *actions, int action_kind, i
     const u128 gen_inc = pcg_make(a.generator[2], a.generator[3]);
     int base = 0;
     bool invalid = false;
+    // several ranges for some element: Generator.choice consumes a data-dependent number of
+    // buffered 32-bit draws before each uniform, so the restarts draw one after another
+    const bool choosing = p.init_options[0] > 1 || p.init_options[1] > 1;
 
     for (int chunk = 0; chunk < p.n; chunk += kEnvPreThreads) {
         const int i = chunk + tid;
@@ -387,15 +439,16 @@ env_pre_kernel(EnvParams p, EnvArrays a, const void *actions, int action_kind, i
         const int rank = base + (warp > 0 ? warp_totals[warp - 1] : 0) +
                          __popc(ballot & ((1u << lane) - 1));
         if (i < p.n) a.reset_rank[i] = done ? rank : -1;
-        if (done) {
-            // RangedInitializer: uniform(low, high, size=(k, 2)) = low + range * double, in
-            // env-major order, rounded to float32 by astype
+        if (done && !choosing) {
+            // RangedInitializer, one range per element: uniform(low, high, size=(k, 2)) =
+            // low + range * double, in env-major order, rounded to float32 by astype - two
+            // draws per restart, so restart r starts 2 r draws into the stream
             u128 state = pcg_advance(gen_state, gen_inc, 2ull * (uint64_t)rank);
 #pragma unroll
             for (int element = 0; element < 2; ++element) {
                 const double unit = pcg_next_double(state, gen_inc);
                 a.new_states[2 * rank + element] = __double2float_rn(
-                    __dadd_rn(p.init_low[element], __dmul_rn(p.init_range[element], unit)));
+                    __dadd_rn(p.init_low[element][0], __dmul_rn(p.init_range[element][0], unit)));
             }
         }
         base += chunk_total;
@@ -403,7 +456,22 @@ env_pre_kernel(EnvParams p, EnvArrays a, const void *actions, int action_kind, i
     }
     if (invalid) atomicExch(&a.counters[1], 1);
     if (tid == 0) {
-        const u128 state = pcg_advance(gen_state, gen_inc, 2ull * (uint64_t)base);
+        u128 state = gen_state;
+        if (choosing) {
+            PcgBuffer buffer{(uint32_t)a.generator[4], (uint32_t)a.generator[5]};
+            for (int r = 0; r < base; ++r) {
+                for (int element = 0; element < 2; ++element) {
+                    const uint32_t k = pcg_choice(state, gen_inc, buffer, (uint32_t)p.init_options[element]);
+                    const double unit = pcg_next_double(state, gen_inc);
+                    a.new_states[2 * r + element] = __double2float_rn(
+                        __dadd_rn(p.init_low[element][k], __dmul_rn(p.init_range[element][k], unit)));
+                }
+            }
+            a.generator[4] = buffer.has;
+            a.generator[5] = buffer.value;
+        } else {
+            state = pcg_advance(gen_state, gen_inc, 2ull * (uint64_t)base);
+        }
         a.generator[0] = (uint64_t)(state >> 64);
         a.generator[1] = (uint64_t)state;
         a.counters[0] = base;

@@ -18,7 +18,7 @@ What is understood (anything else raises ``NotImplementedError`` - use ``VectorE
   a ``DeltaObserver``, optionally under a ``NormalizedObserver``;
 * any ``+`` / ``*`` tree of ``DeltaRewarder``, ``DistanceRewarder``, ``ObservationRewarder``,
   ``OnTargetRewarder``, ``StoppedRewarder`` (up to 8 nodes), with NumPy's result types;
-* initializer ``RangedInitializer`` with one range per element and a PCG64DXSM generator.
+* initializer ``RangedInitializer`` (up to four ranges per element) on a PCG64DXSM generator.
 """
 
 from typing import Any
@@ -224,15 +224,16 @@ def _read_observer(observer, config: _lib.EnvConfig):
 
 def _read_initializer(initializer, config: _lib.EnvConfig):
     # pylint: disable=protected-access
-    if not (isinstance(initializer, state_initializer.RangedInitializer)
-            and len(initializer._ranges) == 2
-            and all(len(options) == 1 for options in initializer._ranges)):
+    if not (isinstance(initializer, state_initializer.RangedInitializer) and len(initializer._ranges) == 2
+            and all(1 <= len(options) <= 4 for options in initializer._ranges)):
         _unsupported("initializer")
     generator = initializer._generator
     if generator.bit_generator.state["bit_generator"] != "PCG64DXSM":
         _unsupported("initializer (its generator must be a PCG64DXSM)")
     for i, options in enumerate(initializer._ranges):
-        config.init_low[i], config.init_high[i] = (float(end) for end in options[0])
+        config.init_options[i] = len(options)
+        for k, (low, high) in enumerate(options):
+            config.init_low[i][k], config.init_high[i][k] = float(low), float(high)
     return generator
 
 
@@ -274,8 +275,9 @@ class DeviceVectorEnvironment(gym_compat.VectorEnv):
         self._discrete = config.transformer in (_lib.ENV_DISCRETE_MOVE, _lib.ENV_DISCRETE_JUMP)
         self._device = torch.device(f"cuda:{renderer.context.device}")
         self._env = _lib.DeviceEnv(renderer.context, config)
-        words = generator.bit_generator.state["state"]
-        self._env.set_generator(int(words["state"]), int(words["inc"]))
+        snapshot = generator.bit_generator.state
+        self._env.set_generator(int(snapshot["state"]["state"]), int(snapshot["state"]["inc"]),
+                                int(snapshot["has_uint32"]), int(snapshot["uinteger"]))
         self._started = False
         self.last_resets = 0
 
@@ -310,8 +312,9 @@ class DeviceVectorEnvironment(gym_compat.VectorEnv):
         self._env.close()
 
     # ------------------------------------------------------------------------- inspection
-    def generator_state(self) -> tuple[int, int]:
-        """(state, increment) of the PCG64DXSM stream the restarts draw from."""
+    def generator_state(self) -> tuple[int, int, int, int]:
+        """(state, increment, has_uint32, uinteger) of the PCG64DXSM stream the restarts draw
+        from, as in numpy's ``bit_generator.state``."""
 
         return self._env.get_generator()
 
@@ -325,8 +328,7 @@ class DeviceVectorEnvironment(gym_compat.VectorEnv):
         state, the initializer's generator and the renderer's RNG states (the reference
         cannot checkpoint an env: its RNG states live in a numba device array)."""
 
-        state, inc = self._env.get_generator()
-        return {"env": self._env.export(), "generator": (state, inc),
+        return {"env": self._env.export(), "generator": self._env.get_generator(),
                 "rng_states": self._renderer.context.rng_export()}
 
     def load_state_dict(self, checkpoint: dict):

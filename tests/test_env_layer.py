@@ -205,8 +205,12 @@ def test_device_env_reads_strategy_trees_and_refuses_the_rest(modules):
     initializers = m.state_initializer
     generator = dve._read_initializer(initializers.RangedInitializer([[(5.0, 10.0)]] * 2, seed=3), config)
     assert generator.bit_generator.state["bit_generator"] == "PCG64DXSM"
-    assert list(config.init_low) == [5.0, 5.0] and list(config.init_high) == [10.0, 10.0]
-    for initializer in (initializers.RangedInitializer([[(5.0, 6.0), (8.0, 9.0)], [(5.0, 10.0)]]),
+    assert [config.init_low[i][0] for i in range(2)] == [5.0, 5.0]
+    assert [config.init_high[i][0] for i in range(2)] == [10.0, 10.0] and list(config.init_options) == [1, 1]
+    dve._read_initializer(initializers.RangedInitializer([[(5.0, 6.0), (8.0, 9.0)], [(5.0, 10.0)]], seed=4), config)
+    assert list(config.init_options) == [2, 1] and list(config.init_low[0][:2]) == [5.0, 8.0]
+    assert list(config.init_high[0][:2]) == [6.0, 9.0]
+    for initializer in (initializers.RangedInitializer([[(5.0, 10.0)] * 5, [(5.0, 10.0)]]),
                         initializers.RangedInitializer([[(5.0, 10.0)]] * 3),
                         initializers.FixedInitializer(numpy.zeros((4, 2))),
                         initializers.RangedInitializer(

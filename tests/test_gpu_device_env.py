@@ -82,8 +82,11 @@ def _strategies(num_envs, renderer, seed, frame_height, kind="steps", max_steps=
         rewarder = (episode_rewarder.ObservationRewarder(1)
                     + episode_rewarder.StoppedRewarder(1, 0.125)
                     * episode_rewarder.OnTargetRewarder((0, 1), 0.25))
+    ranges = [[ENDS]] * 2
+    if kind == "mixed":  # several ranges per element: Generator.choice before every uniform
+        ranges = [[(5.0, 6.0), (9.0, 10.0), (7.0, 7.5)], [(5.0, 7.0), (8.0, 10.0)]]
     return {"ender": ender,
-            "initializer": state_initializer.RangedInitializer([[ENDS]] * 2, generator=_generator(seed)),
+            "initializer": state_initializer.RangedInitializer(ranges, generator=_generator(seed)),
             "observer": observer, "rewarder": rewarder, "transformer": transformer}
 
 
@@ -132,8 +135,9 @@ def _assert_same_rollout(host, device, actions):
         resets += device.last_resets
     exported = device.export_state()
     numpy.testing.assert_array_equal(exported["states"], host._state)
-    host_generator = host._initializer._generator.bit_generator.state["state"]
-    assert device.generator_state() == (host_generator["state"], host_generator["inc"])
+    host_generator = host._initializer._generator.bit_generator.state
+    assert device.generator_state() == (host_generator["state"]["state"], host_generator["state"]["inc"],
+                                        host_generator["has_uint32"], host_generator["uinteger"])
     numpy.testing.assert_array_equal(device._renderer.context.rng_export(0, 4096),
                                      _host_renderer(host._observer).context.rng_export(0, 4096))
     return resets
