@@ -16,7 +16,7 @@ LIB_NAME = "libreinfocus_b200.so"
 LIB_PATH = os.path.join(PACKAGE_DIR, LIB_NAME)
 
 SOURCES = ["rf_api.cu"]
-HEADERS = ["rf_rng.cuh", "rf_tracer.cuh", "rf_focus.cuh", "rf_generic.cuh", "rf_env.cuh"]
+HEADERS = ["rf_rng.cuh", "rf_tracer.cuh", "rf_tracer_mp.cuh", "rf_focus.cuh", "rf_generic.cuh", "rf_env.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -17,6 +17,7 @@
 #include "rf_generic.cuh"
 #include "rf_rng.cuh"
 #include "rf_tracer.cuh"
+#include "rf_tracer_mp.cuh"
 
 #define RF_ABI_VERSION 8
 
@@ -185,30 +186,32 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
     // step latency)
     int contexts = ctx->trace_contexts;
     if (contexts < 0)
-        contexts = p.total >= (int64_t)ctx->prop.multiProcessorCount * 9216 ? rf::kMcDefaultContexts : 0;
-    if (!fast || H > rf::kMcMaxFrame || W > rf::kMcMaxFrame) contexts = 0;
+        contexts = p.total >= (int64_t)ctx->prop.multiProcessorCount * 9216 ? rf::kMpDefaultContexts : 0;
+    if (!fast || H > rf::kMpMaxFrame || W > rf::kMpMaxFrame) contexts = 0;
     if (contexts > 0) {
-        // multi-context kernel: blocks are per env, kCtx * kMcThreads pixels each
-        const int per_block = contexts * rf::kMcThreads;
+        // multi-pixel kernel: blocks are per env, kCtx * kThreads pixels each (57 KB of shared
+        // memory at 7 x 256 and at 8 x 224: four blocks per SM either way)
+        const int threads = contexts == 8 ? 224 : 256;
+        const int per_block = contexts * threads;
         const int blocks_per_env = (H * W + per_block - 1) / per_block;
         const int64_t grid = (int64_t)n * blocks_per_env;
         if (grid > 0x7fffffffLL) return fail(ctx, RF_ERR_INVALID, "render batch too large");
-        const size_t smem = (size_t)per_block * sizeof(rf::McSlots);
+        const size_t smem = (size_t)per_block * 32;
         auto launch = [&](auto kernel) -> int {
             if (smem > 48 * 1024)
                 RF_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kernel<<<(unsigned)grid, rf::kMcThreads, smem, stream>>>(p, blocks_per_env);
+            kernel<<<(unsigned)grid, threads, smem, stream>>>(p, blocks_per_env);
             return RF_OK;
         };
         int rc = RF_OK;
         switch (contexts) {
-            case 2: rc = launch(rf::trace_mc_kernel<2>); break;
-            case 3: rc = launch(rf::trace_mc_kernel<3>); break;
-            case 4: rc = launch(rf::trace_mc_kernel<4>); break;
-            case 5: rc = launch(rf::trace_mc_kernel<5>); break;
-            case 6: rc = launch(rf::trace_mc_kernel<6>); break;
-            case 7: rc = launch(rf::trace_mc_kernel<7>); break;
-            case 8: rc = launch(rf::trace_mc_kernel<8>); break;
+            case 2: rc = launch(rf::trace_mp_kernel<2, 256>); break;
+            case 3: rc = launch(rf::trace_mp_kernel<3, 256>); break;
+            case 4: rc = launch(rf::trace_mp_kernel<4, 256>); break;
+            case 5: rc = launch(rf::trace_mp_kernel<5, 256>); break;
+            case 6: rc = launch(rf::trace_mp_kernel<6, 256>); break;
+            case 7: rc = launch(rf::trace_mp_kernel<7, 256>); break;
+            case 8: rc = launch(rf::trace_mp_kernel<8, 224>); break;
             default:
                 return fail(ctx, RF_ERR_INVALID, "unsupported context count %d", contexts);
         }

@@ -221,7 +221,7 @@ def test_frames_beyond_the_multi_pixel_kernels_coordinate_range(torch):
 
 
 def test_pixels_per_thread_follow_the_batch_size(torch):
-    """Default option: one pixel per thread for latency-bound small batches, seven once
+    """Default option: one pixel per thread for latency-bound small batches, eight once
     the batch fills the GPU a few times over; both leave the same frames as the oracle
     (covered above), here only the choice is checked."""
 
@@ -231,7 +231,7 @@ def test_pixels_per_thread_follow_the_batch_size(torch):
     assert small.context.last_trace_kernel() == 1
     large.update_targets([7.0] * 24), large.update_focus_planes([6.0] * 24)
     large.render_gray_device(300)
-    assert large.context.last_trace_kernel() == 7
+    assert large.context.last_trace_kernel() == 8
 
 
 def test_literal_kernel_handles_a_non_default_camera(torch):
@@ -424,7 +424,7 @@ def test_full_benchmark_batch_matches_oracle_on_sampled_envs(torch):
     sampled = [0, 1, 512, 513, 2047, 3333, 4095]
     before = {e: ctx.rng_export(e * pixels, pixels) for e in sampled}
     focus = renderer.step_focus(targets, planes, height)
-    assert ctx.last_trace_kernel() == 7 and ctx.last_focus_kernel() == 1
+    assert ctx.last_trace_kernel() == 8 and ctx.last_focus_kernel() == 1
     assert focus.shape == (n,) and numpy.isfinite(focus).all()
     world, cam = oracle.pack_world(targets), oracle.pack_cameras(planes)
     for e in sampled:
