@@ -13,6 +13,10 @@ envs in total (strong scaling: each rank owns 4096/N envs).
 `roofline`: the tracer kernel (dominant) against the FP32 FFMA peak measured live.
 `cpu_baseline` / `--impl reference`: the CPU oracle (C restatement of the reference, all
             host cores) on a bounded sample of the same workload.
+`numba_cuda_baseline`: the UNMODIFIED reference (baseline/_ref) with its numba-CUDA kernel and
+            cv2 focus loop on this same GPU, in this same run, after the timed regions
+            (N = 1 only); `cudasim_baseline`: the reference under NUMBA_ENABLE_CUDASIM=1 on
+            one host core at a reduced frame. Reported baselines, not targets.
 """
 
 import argparse
@@ -124,6 +128,67 @@ def cpu_baseline(steps, warmup, cores_hint=None):
         "sample": f"{sample_envs} envs x {HEIGHT}x{HEIGHT} x {SPP} spp per step "
                   f"({sample_envs * HEIGHT * HEIGHT * SPP:.3g} rays), {steps} timed steps",
         "ms_per_step": mean * 1e3,
+    }
+
+
+def _run_json(cmd, env=None, timeout=600):
+    """Runs a helper script and returns the JSON object on its last stdout line."""
+
+    try:
+        done = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=REPO)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"timed out after {timeout} s"}
+    lines = [line for line in done.stdout.splitlines() if line.startswith("{")]
+    if done.returncode != 0 or not lines:
+        tail = (done.stderr or done.stdout).strip().splitlines()[-1:] or ["no output"]
+        return {"unavailable": f"exit {done.returncode}: {tail[0][:200]}"}
+    return json.loads(lines[-1])
+
+
+def numba_cuda_baseline(gpu_index, envs, steps):
+    """The unmodified reference's numba-CUDA path on this GPU, in this run: FastRenderer +
+    vision.focus_values driven as FocusObserver.observe does (baseline/run_numba_cuda.py).
+    Steady-state steps only; the first call (JIT + sequential RNG-state init) is listed
+    separately. `envs` is a bounded sample: the path's cost is linear in the env count."""
+
+    if not os.path.isdir(os.path.join(REPO, "baseline", "_ref", "reinfocus")):
+        return {"unavailable": "baseline/_ref (copy of the reference) is not present"}
+    env = dict(os.environ)
+    env["CUDA_VISIBLE_DEVICES"] = str(gpu_index) if "CUDA_VISIBLE_DEVICES" not in env else env["CUDA_VISIBLE_DEVICES"]
+    env.pop("NUMBA_ENABLE_CUDASIM", None)
+    with ClockSampler(gpu_index) as clocks:
+        result = _run_json([sys.executable, os.path.join("baseline", "run_numba_cuda.py"), "--envs", str(envs),
+                            "--steps", str(steps), "--warmup", "1", "--height", str(HEIGHT), "--spp", str(SPP)],
+                           env=env, timeout=900)
+    if "unavailable" in result:
+        return result
+    return {
+        "value": result["env_steps_per_s"], "unit": UNIT, "measured_in_run": True,
+        "what": "unmodified reference: numba-CUDA FastRenderer.render + cv2 vision.focus_values, same GPU",
+        "sample": f"{envs} envs x {HEIGHT}x{HEIGHT} x {SPP} spp per step, {steps} timed steps after 1 warm-up",
+        "ms_per_step": result["mean_s"]["step"] * 1e3,
+        "breakdown_ms": {k: v * 1e3 for k, v in result["mean_s"].items()},
+        "rays_per_s_render_call": result["rays_per_s_render_call"],
+        "first_call_s_incl_jit_and_rng_init": result["first_call_s_incl_jit_and_rng_init"],
+        "clocks": clocks.summary(),
+    }
+
+
+def cudasim_baseline():
+    """The reference under NUMBA_ENABLE_CUDASIM=1 (its CPU path) on one host core, reduced
+    frame, rate extrapolated to the full frame (baseline/run_cudasim.py)."""
+
+    env = dict(os.environ)
+    env["NUMBA_ENABLE_CUDASIM"] = "1"
+    result = _run_json([sys.executable, os.path.join("baseline", "run_cudasim.py"), "--envs", "1",
+                        "--height", "32", "--spp", "4"], env=env, timeout=600)
+    if "unavailable" in result:
+        return result
+    return {
+        "value": result["env_steps_per_s_extrapolated"], "unit": UNIT, "measured_in_run": True,
+        "what": "unmodified reference under NUMBA_ENABLE_CUDASIM=1 (one Python thread per CUDA thread)",
+        "sample": f"1 env x 32x32 x 4 spp ({result['rays']} rays), extrapolated to {result['extrapolated_to']}",
+        "rays_per_s": result["rays_per_s"], "cores": 1, "nproc": result["nproc"],
     }
 
 
@@ -328,6 +393,8 @@ def run_ours(args):
         "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": device_ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32+f64+u64", "data": "synthetic",
+        "scene": "static (`value` re-renders one scene from HBM-resident parameters; `e2e` takes new host "
+                 "targets / focus planes every step)",
         "config": {
             "workload": f"DiscreteSteps-v0 hot path (FocusObserver.observe): {args.envs} envs "
                         f"sharded over {world_size} GPU(s), {HEIGHT}x{HEIGHT}, {SPP} spp, "
@@ -349,7 +416,8 @@ def run_ours(args):
             "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / fp32_peak if fp32_peak else None,
             "traffic": scaled_traffic("trace_kernel_bytes_per_env"),
-            "traffic_source": "ncu dram bytes per env at 256 envs (profiles/ncu_traffic.json) x envs per launch",
+            "traffic_source": traffic.get("note", "static ncu capture (profiles/ncu_traffic.json)") +
+                              "; scaled by envs per launch",
             "algorithmic_bytes_per_launch": n_local * HEIGHT * HEIGHT * 33,
             "peak_source": f"FFMA loop measured live on this GPU (implies {implied_mhz:.0f} MHz); "
                            f"theoretical 148 SM x 128 x 2 x 1.965 GHz = {THEORETICAL_FP32_TFLOPS:.1f}",
@@ -389,10 +457,15 @@ def run_ours(args):
     }
     if base is not None:
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    numba_path = os.path.join(REPO, "profiles", "numba_cuda_baseline.json")
-    if os.path.exists(numba_path):
-        with open(numba_path) as f:
-            line["numba_cuda_baseline"] = json.load(f)
+    if world_size == 1 and not args.no_reference_baselines:
+        # the reference itself, same run, same GPU (after every timed region of this arm)
+        ctx.rng_reset()  # hand the 5.9 GB of RNG states back before the reference allocates its own
+        torch.cuda.empty_cache()
+        line["numba_cuda_baseline"] = numba_cuda_baseline(local_rank, args.numba_envs, 3)
+        if "value" in line["numba_cuda_baseline"]:
+            line["vs_numba_cuda"] = line["value"] / line["numba_cuda_baseline"]["value"]
+            line["e2e"]["vs_numba_cuda"] = line["e2e"]["value"] / line["numba_cuda_baseline"]["value"]
+        line["cudasim_baseline"] = cudasim_baseline()
     emit(line)
     if world_size > 1:
         dist.destroy_process_group()
@@ -407,8 +480,8 @@ def issue_view(traffic, n_local, trace_ms, sm_count, clock_summary):
     peak = sm_count * 4 * mhz * 1e6 / 1e9
     return {"warp_inst_per_launch": per_env * n_local, "achieved": achieved, "peak": peak,
             "unit": "G warp-inst/s", "frac": achieved / peak,
-            "source": "smsp__inst_executed.sum per env from ncu at 256 envs (profiles/ncu_traffic.json); "
-                      "peak = SMs x 4 schedulers x sampled SM clock",
+            "source": "static ncu capture: smsp__inst_executed.sum per env at 256 envs "
+                      "(profiles/ncu_traffic.json); peak = SMs x 4 schedulers x sampled SM clock",
             "ncu_pct": traffic.get("trace_kernel_ncu_pct")}
 
 
@@ -439,6 +512,10 @@ def main():
     parser.add_argument("--envs", type=int, default=4096)
     parser.add_argument("--impl", choices=["ours", "reference"], default="ours")
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--no-reference-baselines", action="store_true",
+                        help="skip the numba-CUDA and CUDASIM legs (the unmodified reference, N = 1 only)")
+    parser.add_argument("--numba-envs", type=int, default=512,
+                        help="env count of the numba-CUDA leg (its sequential RNG init costs 30 us per env-pixel row)")
     parser.add_argument("--contexts", type=int, default=None,
                         help="pixels per thread of the tracer (0, 2..8); default: library default")
     args = parser.parse_args()

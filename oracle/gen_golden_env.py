@@ -226,5 +226,83 @@ def run_gpu():
     print("done single")
 
 
+def rollout_with_renders(env, actions, vector=True, render_every=4, render_phase=1):
+    """Vector-env rollout with env.render() interleaved (HistoryVisualizer.visualize ->
+    renderer.render(600) through the SHARED renderer, reference episode_visualizer.py:197):
+    the 600-px render re-creates the RNG states (render.py:256-257) and advances them, which
+    changes every later observation. Records the sequences plus the sha256 of the rendered
+    scene part (left 600 columns) of every frame."""
+
+    import hashlib
+
+    import numpy
+
+    obs, _ = env.reset()
+    out = {"obs0": numpy.asarray(obs), "actions": actions}
+    rows = {"obs": [], "rew": [], "term": [], "trunc": []}
+    shas, shapes, at = [], [], []
+    for step, action in enumerate(actions):
+        o, r, te, tr, _ = env.step(action)
+        rows["obs"].append(numpy.array(o, copy=True))
+        rows["rew"].append(numpy.array(r, copy=True))
+        rows["term"].append(numpy.array(te, copy=True))
+        rows["trunc"].append(numpy.array(tr, copy=True))
+        if not vector and (te or tr):
+            o, _ = env.reset()
+            rows["obs"][-1] = numpy.array(o, copy=True)  # observation after the manual reset
+        if step % render_every == render_phase:
+            frame = env.render()
+            scene = numpy.ascontiguousarray(frame[:, :600])
+            shas.append(hashlib.sha256(scene.tobytes()).hexdigest())
+            shapes.append(scene.shape)
+            at.append(step)
+    out.update({k: numpy.stack(v) for k, v in rows.items()})
+    out.update({"render_sha256": numpy.array(shas), "render_shape": numpy.array(shapes),
+                "render_at": numpy.array(at)})
+    return out
+
+
+def run_gpu_visualizer():
+    """The reference's VectorDiscreteSteps(render_mode="rgb_array") with renders between the
+    steps, numba-CUDA on the GPU box. matplotlib is not installable offline, so the graph
+    panel of HistoryVisualizer is replaced by a blank image; its renderer.render(600) call -
+    the part with side effects on the env - is the reference's own."""
+
+    import numpy
+
+    sys.path.insert(0, os.path.join(REPO, "baseline", "_ref"))
+    import oracle.cudasim_shim as shim
+
+    shim.install_gym_stub()
+    shim.install_plot_stub()
+    from examples import custom_environments as reference_envs  # baseline/_ref/examples
+    from reinfocus.environments import episode_visualizer
+
+    def blank_panel(self, env_index, frame_height=600):
+        return numpy.full((frame_height, frame_height * 4 // 3, 3), 255, dtype=numpy.uint8)
+
+    episode_visualizer.HistoryVisualizer._visualize_single_history = blank_panel
+
+    out_dir = os.path.join(REPO, "gpurun_out", "golden_gpu")
+    os.makedirs(out_dir, exist_ok=True)
+    # One env per vector env: with render_mode="rgb_array" the reference's
+    # HistoryVisualizer.reset appends the focus history without its `indices`
+    # (episode_visualizer.py:186), so a restart of only some envs raises in numpy.hstack;
+    # restarts of all envs at once (always the case with one env) work.
+    env = reference_envs.VectorDiscreteSteps(max_episode_steps=7, num_envs=1, render_mode="rgb_array")
+    _seed_initializer(env, 79)
+    actions = numpy.random.Generator(numpy.random.PCG64(7)).integers(0, 13, (26, 1))
+    data = rollout_with_renders(env, actions, True)
+    numpy.savez_compressed(os.path.join(out_dir, "gpu_env_vector_with_renders.npz"), **data)
+    print("done vector + visualizer", data["render_shape"].tolist(), int(data["trunc"].sum()), "truncations")
+
+    env = reference_envs.DiscreteSteps(render_mode="rgb_array")
+    _seed_initializer(env, 80)
+    actions = numpy.random.Generator(numpy.random.PCG64(8)).integers(0, 13, 30)
+    data = rollout_with_renders(env, actions, False, render_every=3, render_phase=0)
+    numpy.savez_compressed(os.path.join(out_dir, "gpu_env_single_with_renders.npz"), **data)
+    print("done single + visualizer", data["render_shape"].tolist(), int(data["term"].sum()), "terminations")
+
+
 if __name__ == "__main__":
-    {"sim": run_sim, "gpu": run_gpu}[sys.argv[1]]()
+    {"sim": run_sim, "gpu": run_gpu, "gpu_vis": run_gpu_visualizer}[sys.argv[1]]()

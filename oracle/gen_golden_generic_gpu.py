@@ -14,11 +14,25 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(REPO, "gpurun_out", "golden_gpu")
 
 
-def scenes(sf, camera):
-    """name -> (list of per-env shape lists, list of per-env camera kwargs, frame_shape, spp)"""
+def scenes(sf, camera, graphics=None):
+    """name -> (list of per-env shape lists, list of per-env camera kwargs, frame_shape, spp).
+    `graphics`: the package's sphere / rectangle / vector modules (for the hand-built scene)."""
 
     P = sf.ShapeParameters
+    extra = {}
+    if graphics is not None:
+        sphere, rectangle, vector = graphics
+        # three shapes per env, odd frame size, varied cameras: nothing the factories build
+        extra["three_shapes"] = (
+            [[sphere.sphere(vector.v3f(-1.5, 0.5, -7.0), 1.25, vector.v2f(6, 10)),
+              rectangle.rectangle(vector.v2f(-0.5, 2.5), vector.v2f(-2.0, 0.25), -9.0, vector.v2f(5, 3)),
+              sphere.sphere(vector.v3f(1.0, -0.75, -4.0), 0.5)],
+             sf.two_rect(P(9.0, texture_f=(7, 7)), P(4.5))],
+            [dict(aperture=0.4, focus_distance=6.0, vfov=45),
+             dict(look_from=(-0.2, 0.1, 0.3), aspect_ratio=1.25)],
+            (37, 53), 9)
     return {
+        **extra,
         "one_rect": ([sf.one_rect(P(r_size=30))], [dict()], (40, 60), 8),
         "two_rect": ([sf.two_rect()], [dict(focus_distance=5.0)], (30, 44), 6),
         "one_sphere": ([sf.one_sphere()], [dict()], (40, 60), 8),
@@ -39,11 +53,15 @@ def main():
     import numpy
     from numba import cuda
 
-    from reinfocus.graphics import camera, render, shape_factory, world
+    from reinfocus.graphics import camera, rectangle, render, shape_factory, sphere, world
     from reinfocus.graphics import vector
 
+    only = set(sys.argv[1:])
     os.makedirs(OUT, exist_ok=True)
-    for name, (env_shapes, cam_kwargs, frame_shape, spp) in scenes(shape_factory, camera).items():
+    for name, (env_shapes, cam_kwargs, frame_shape, spp) in scenes(
+            shape_factory, camera, (sphere, rectangle, vector)).items():
+        if only and name not in only:
+            continue
         cams = []
         for kw in cam_kwargs:
             kw = dict(kw)
@@ -67,6 +85,8 @@ def main():
         numpy.savez_compressed(os.path.join(OUT, f"gpu_generic_{name}.npz"), **out)
         print("done", name, frames.shape, out["channel_means"][0], flush=True)
 
+    if only:
+        return
     kernel = render.device_render
     for _, ptx in kernel.inspect_asm().items():
         open(os.path.join(OUT, "numba_generic_render.ptx"), "w").write(ptx)

@@ -642,15 +642,17 @@ def _env_gold(name):
 
 
 def _compare_rollout(got, gold):
-    for key in ("term", "trunc"):
-        numpy.testing.assert_array_equal(got[key], gold[key], err_msg=key)
-    # observations / rewards are float32 functions of float64 focus values; ours is the
-    # exactly rounded variance while numpy.var() may sit an ulp off, so allow one float32 ulp
-    for key in ("obs0", "obs", "rew"):
-        assert got[key].dtype == gold[key].dtype
-        numpy.testing.assert_allclose(got[key], gold[key], rtol=0, atol=2.5e-7, err_msg=key)
-    exact = numpy.mean(got["obs"] == gold["obs"])
-    assert exact > 0.999, f"only {exact:.4%} of observations are bit-identical"
+    """Terminations, truncations, observations and rewards identical to the reference's run.
+    (The focus value under every observation is the exactly rounded variance here and numpy's
+    pairwise float64 `var()` in the reference: the two sit within 2 ulp of each other in
+    float64 and the observers cast to float32, so a difference can survive only when the
+    float64 value lies within ~1e-16 relative of a float32 rounding boundary - about one
+    observation in 1e8. The goldens hold a few thousand: every one must match.)"""
+
+    for key in ("term", "trunc", "obs0", "obs", "rew"):
+        assert got[key].dtype == gold[key].dtype and got[key].shape == gold[key].shape, key
+        mismatches = int((got[key] != gold[key]).sum())
+        assert mismatches == 0, f"{key}: {mismatches} of {gold[key].size} values differ from the reference"
 
 
 def test_vector_discrete_steps_sequences_match_reference(torch):
@@ -682,6 +684,57 @@ def test_discrete_steps_sequences_match_reference(torch):
     _compare_rollout(got, gold)
 
 
+@pytest.mark.parametrize("kind", ["vector", "single"])
+def test_sequences_with_interleaved_visualizer_renders_match_reference(torch, kind):
+    """env.render() between steps goes through HistoryVisualizer.visualize ->
+    renderer.render(600) on the renderer the observer shares (reference
+    episode_visualizer.py:197): it re-creates the RNG states at 600 x 600 (render.py:256-257)
+    and advances them, so every later observation depends on it. Sequences and the rendered
+    scenes against the reference's numba-CUDA run on a B200 (one env per env object: the
+    reference's visualizer cannot take a restart of only some envs, see the generator)."""
+
+    from examples import custom_environments
+    from oracle import gen_golden_env
+
+    gold = _env_gold(f"{kind}_with_renders")
+    if kind == "vector":
+        env = custom_environments.VectorDiscreteSteps(max_episode_steps=7, num_envs=1, render_mode="rgb_array")
+        gen_golden_env._seed_initializer(env, 79)
+        got = gen_golden_env.rollout_with_renders(env, gold["actions"], True)
+        assert gold["trunc"].any()
+    else:
+        env = custom_environments.DiscreteSteps(render_mode="rgb_array")
+        gen_golden_env._seed_initializer(env, 80)
+        got = gen_golden_env.rollout_with_renders(env, gold["actions"], False, render_every=3, render_phase=0)
+    assert len(gold["render_at"]) >= 5
+    numpy.testing.assert_array_equal(got["render_at"], gold["render_at"])
+    numpy.testing.assert_array_equal(got["render_shape"], gold["render_shape"])
+    assert got["render_sha256"].tolist() == gold["render_sha256"].tolist()
+    _compare_rollout(got, gold)
+
+
+def test_reference_env_layer_on_the_c_abi_binding(torch):
+    """INTEGRATION.md section B executed: the reference's own FocusObserver / VectorEnvironment /
+    VectorDiscreteSteps (baseline/_ref, unmodified) with only graphics.render and vision bound
+    to the C-ABI (examples/reference_binding), replaying the reference's B200 sequence."""
+
+    import json
+    import subprocess
+    import sys
+
+    if not os.path.isdir(os.path.join(REPO, "baseline", "_ref", "reinfocus")):
+        pytest.skip("baseline/_ref (copy of the reference) is not present")
+    _env_gold("vector_discrete_steps")
+    done = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "run_reference_binding.py")],
+                          capture_output=True, text=True, timeout=600, cwd=REPO)
+    assert done.returncode == 0, done.stderr[-2000:]
+    result = json.loads([line for line in done.stdout.splitlines() if line.startswith("{")][-1])
+    assert result["env_class"].endswith("VectorDiscreteSteps")
+    assert result["observer_module"].startswith(os.path.join("baseline", "_ref"))
+    for key in ("obs0", "obs", "rew", "term", "trunc"):
+        assert result[f"{key}_mismatches"] == 0, result
+
+
 def test_registry_makes_the_example_envs(torch):
     import examples  # noqa: F401
     from reinfocus_b200 import gym_compat
@@ -699,9 +752,10 @@ def test_registry_makes_the_example_envs(torch):
 
 def _generic_scene(name):
     from oracle import gen_golden_generic_gpu
-    from reinfocus_b200.graphics import camera, shape_factory, vector, world
+    from reinfocus_b200.graphics import camera, rectangle, shape_factory, sphere, vector, world
 
-    env_shapes, cam_kwargs, frame_shape, spp = gen_golden_generic_gpu.scenes(shape_factory, camera)[name]
+    env_shapes, cam_kwargs, frame_shape, spp = gen_golden_generic_gpu.scenes(
+        shape_factory, camera, (sphere, rectangle, vector))[name]
     cams = []
     for kw in cam_kwargs:
         kw = dict(kw)
@@ -713,7 +767,7 @@ def _generic_scene(name):
 
 
 GENERIC_SCENES = ["one_rect", "two_rect", "one_sphere", "two_sphere", "mixed_batch", "ref_test_sphere",
-                  "default_size"]
+                  "default_size", "three_shapes"]
 
 
 @pytest.mark.parametrize("name", GENERIC_SCENES)
@@ -749,11 +803,12 @@ def test_generic_render_reference_average_colour_tests(torch):
     means = frames.reshape(-1, 3).mean(axis=0)
     assert 0.25 * 255 <= means[0] <= 0.5 * 255 and 0.25 * 255 <= means[1] <= 0.5 * 255
     assert means[2] == 0
-    # test_average_colour: a sphere in front of the sky
-    frames = render.render(world.Worlds(shape_factory.one_sphere()), camera.Cameras(camera.make_gpu_camera()),
-                           frame_shape=(100, 200), samples_per_pixel=10)
+    # test_average_colour: an r_size=30 sphere in front of the sky, the reference's own scene,
+    # frame shape and sample count (render_test.py:57-80)
+    frames = render.render(world.Worlds(shape_factory.one_sphere(shape_factory.ShapeParameters(r_size=30))),
+                           camera.Cameras(camera.make_gpu_camera()), frame_shape=(300, 300))
     means = frames.reshape(-1, 3).mean(axis=0) / 255
-    assert 0.4 <= means[0] <= 0.6 and 0.4 <= means[1] <= 0.6 and 0.1 <= means[2] <= 0.2 or means[2] > 0.1
+    assert 0.4 <= means[0] <= 0.6 and 0.4 <= means[1] <= 0.6 and 0.1 <= means[2] <= 0.2, means
 
 
 def test_generic_render_matches_oracle_on_a_random_scene(torch):
