@@ -24,6 +24,9 @@ def main():
     parser.add_argument("--height", type=int, default=300)
     parser.add_argument("--spp", type=int, default=100)
     parser.add_argument("--out", default=None)
+    parser.add_argument("--generic-calls", type=int, default=0,
+                        help="also time render.render (general scenes, reference render.py:88-119) on its "
+                             "default 300 x 600 x 100 spp frame of shape_factory.mixed(), this many calls")
     args = parser.parse_args()
 
     import numpy
@@ -67,6 +70,22 @@ def main():
         "rays_per_s_render_call": rays / mean["render"],
         "focus_sample": [float(f) for f in focus[:4]],
     }
+    if args.generic_calls:
+        from reinfocus.graphics import camera, shape_factory, world
+
+        worlds = world.Worlds(shape_factory.mixed())
+        cameras = camera.Cameras(camera.make_gpu_camera())
+        render.render(worlds, cameras)  # JIT
+        times = []
+        for _ in range(args.generic_calls):
+            t0 = time.perf_counter()
+            frames = render.render(worlds, cameras)
+            times.append(time.perf_counter() - t0)
+        result["generic"] = {"scene": "shape_factory.mixed(), one env, 300 x 600, 100 spp (render.render defaults)",
+                             "calls": args.generic_calls, "mean_s": float(numpy.mean(times)),
+                             "min_s": float(numpy.min(times)),
+                             "rays_per_s": 300 * 600 * 100 / float(numpy.mean(times)),
+                             "mean_colour": [float(c) for c in frames.reshape(-1, 3).mean(axis=0)]}
     line = json.dumps(result)
     print(line)
     if args.out:

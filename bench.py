@@ -158,7 +158,8 @@ def numba_cuda_baseline(gpu_index, envs, steps):
     env.pop("NUMBA_ENABLE_CUDASIM", None)
     with ClockSampler(gpu_index) as clocks:
         result = _run_json([sys.executable, os.path.join("baseline", "run_numba_cuda.py"), "--envs", str(envs),
-                            "--steps", str(steps), "--warmup", "1", "--height", str(HEIGHT), "--spp", str(SPP)],
+                            "--steps", str(steps), "--warmup", "1", "--height", str(HEIGHT), "--spp", str(SPP),
+                            "--generic-calls", "3"],
                            env=env, timeout=900)
     if "unavailable" in result:
         return result
@@ -170,8 +171,52 @@ def numba_cuda_baseline(gpu_index, envs, steps):
         "breakdown_ms": {k: v * 1e3 for k, v in result["mean_s"].items()},
         "rays_per_s_render_call": result["rays_per_s_render_call"],
         "first_call_s_incl_jit_and_rng_init": result["first_call_s_incl_jit_and_rng_init"],
+        "generic": result.get("generic"),
         "clocks": clocks.summary(),
     }
+
+
+def generic_leg(calls=5):
+    """render.render on its defaults (general scenes: spheres + rectangles, 50 bounces; reference
+    graphics/render.py:88-119): shape_factory.mixed(), one env, 300 x 600, 100 spp. `ms_per_call` is the
+    public API (host scene in, host frames out), `kernel_ms` the tracer launch alone."""
+
+    import numpy
+    import torch
+
+    from reinfocus_b200 import _lib
+    from reinfocus_b200.graphics import camera, render, shape_factory, world
+
+    worlds = world.Worlds(shape_factory.mixed())
+    cameras = camera.Cameras(camera.make_gpu_camera())
+    height, width, spp = 300, 600, 100
+    render.render(worlds, cameras)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(calls):
+        t0 = time.perf_counter()
+        frames = render.render(worlds, cameras)
+        times.append(time.perf_counter() - t0)
+    ctx = _lib.shared_context()
+    parameters, types, sizes = worlds.device_data()
+    if parameters.shape[2] < 7:
+        parameters = numpy.pad(parameters, ((0, 0), (0, 0), (0, 7 - parameters.shape[2])))
+    out = torch.empty((1, height, width, 3), dtype=torch.uint8, device="cuda")
+    kernel = []
+    for _ in range(calls):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.render_generic(parameters, types, sizes, cameras.device_data()[:1], height, width, spp,
+                           out.data_ptr(), seed=0)
+        e1.record()
+        torch.cuda.synchronize()
+        kernel.append(e0.elapsed_time(e1))
+    rays = height * width * spp
+    return {"what": "render.render defaults: shape_factory.mixed(), 1 env, 300 x 600, 100 spp, host frames out",
+            "ms_per_call": float(numpy.mean(times)) * 1e3, "device_ms": float(numpy.mean(kernel)),
+            "rays_per_s": rays / float(numpy.mean(times)),
+            "rays_per_s_device": rays / (float(numpy.mean(kernel)) * 1e-3),
+            "mean_colour": [float(c) for c in frames.reshape(-1, 3).mean(axis=0)]}
 
 
 def cudasim_baseline():
@@ -457,6 +502,8 @@ def run_ours(args):
     }
     if base is not None:
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if world_size == 1:
+        line["generic"] = generic_leg()
     if world_size == 1 and not args.no_reference_baselines:
         # the reference itself, same run, same GPU (after every timed region of this arm)
         ctx.rng_reset()  # hand the 5.9 GB of RNG states back before the reference allocates its own
@@ -465,6 +512,9 @@ def run_ours(args):
         if "value" in line["numba_cuda_baseline"]:
             line["vs_numba_cuda"] = line["value"] / line["numba_cuda_baseline"]["value"]
             line["e2e"]["vs_numba_cuda"] = line["e2e"]["value"] / line["numba_cuda_baseline"]["value"]
+            numba_generic = line["numba_cuda_baseline"].get("generic")
+            if numba_generic:
+                line["generic"]["vs_numba_cuda"] = numba_generic["mean_s"] * 1e3 / line["generic"]["ms_per_call"]
         line["cudasim_baseline"] = cudasim_baseline()
     emit(line)
     if world_size > 1:

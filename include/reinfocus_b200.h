@@ -196,9 +196,9 @@ int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float 
  *   ender        any tree of TimeLimitEnder, DivergingEnder, OnTargetEnder, StoppedEnder,
  *                EndlessEnder combined with & and | (episode_ender.py:112-656), given as a
  *                postfix program of rf_env_ender nodes
- *   observer     IndexedElementObservers and one FocusObserver side by side, optionally
- *                under a DeltaObserver, optionally under a NormalizedObserver
- *                (state_observer.py:103-517)
+ *   observer     any tree of DeltaObservers and NormalizedObservers over
+ *                IndexedElementObservers and one FocusObserver (state_observer.py:103-517),
+ *                given as a postfix program of rf_env_observer nodes
  *   rewarder     any tree of DeltaRewarder, DistanceRewarder, ObservationRewarder,
  *                OnTargetRewarder, StoppedRewarder combined with + and *
  *                (episode_rewarder.py:86-429), as a postfix program of rf_env_reward nodes;
@@ -231,6 +231,16 @@ typedef struct {
     float f0, f1;
     double d0, d1;
 } rf_env_reward;
+/* One node of the observer program, children before parents. ELEMENT: arg = the state
+ * element an IndexedElementObserver shows. FOCUS: the FocusObserver (exactly one per
+ * program). DELTA / NORMALIZED: arg = number of child observers (their observations side by
+ * side, as WrapperObserver stacks them); DELTA: flag = include_original; NORMALIZED: offset =
+ * first of its columns in obs_mid / obs_scale (one (_mid, _scale) pair per column it sees). */
+enum { RF_ENV_OBS_ELEMENT = 0, RF_ENV_OBS_FOCUS = 1, RF_ENV_OBS_DELTA = 2, RF_ENV_OBS_NORMALIZED = 3 };
+typedef struct {
+    int kind, arg, flag, offset;
+} rf_env_observer;
+enum { RF_ENV_MAX_NODES = 24, RF_ENV_MAX_OBS_NODES = 16, RF_ENV_MAX_OBS_DIM = 16, RF_ENV_MAX_OBS_VALUES = 32 };
 enum { RF_ENV_ACTIONS_INT32 = 0, RF_ENV_ACTIONS_INT64 = 1, RF_ENV_ACTIONS_FLOAT32 = 2 };
 typedef struct {
     int num_envs, frame_height, samples_per_pixel;
@@ -242,17 +252,16 @@ typedef struct {
     float jump_threshold;    /* jumps / continuous moves shorter than this are ignored */
     float move_speed;        /* RF_ENV_CONTINUOUS_MOVE: distance of action 1.0 */
     float jumps[32];         /* RF_ENV_DISCRETE_JUMP: positions, float32 as the reference keeps them */
-    int n_enders, n_rewards; /* program lengths, 1..8 each */
-    rf_env_ender enders[8];
-    rf_env_reward rewards[8];
-    /* observer: n_base (1..4) base observers side by side, base_index = the state element an
-     * IndexedElementObserver shows or -1 for the FocusObserver (exactly one); obs_delta: they
-     * sit under a DeltaObserver (obs_original: with include_original); obs_normalized: a
-     * NormalizedObserver on top, with its _mid / _scale per output column. The observation
-     * has n_base columns, times two for a DeltaObserver with include_original. */
-    int n_base, base_index[4];
-    int obs_delta, obs_original, obs_normalized;
-    float obs_mid[8], obs_scale[8];
+    int n_enders, n_rewards; /* program lengths, 1..RF_ENV_MAX_NODES each */
+    rf_env_ender enders[RF_ENV_MAX_NODES];
+    rf_env_reward rewards[RF_ENV_MAX_NODES];
+    /* observer program (1..RF_ENV_MAX_OBS_NODES nodes; the root is the last node). An
+     * observation has at most RF_ENV_MAX_OBS_DIM columns and no more than
+     * RF_ENV_MAX_OBS_VALUES values are alive at any point of the program. obs_mid /
+     * obs_scale: the NormalizedObservers' _mid / _scale rows, at their nodes' offsets. */
+    int n_observers;
+    rf_env_observer observers[RF_ENV_MAX_OBS_NODES];
+    float obs_mid[RF_ENV_MAX_OBS_VALUES], obs_scale[RF_ENV_MAX_OBS_VALUES];
     /* RangedInitializer: per state element 1..4 (low, high) ranges; with several, the range
      * is picked like Generator.choice does before Generator.uniform draws inside it */
     int init_options[2];
@@ -282,10 +291,12 @@ int rf_env_step(rf_env *env, const void *d_actions, int action_kind, float *d_ob
  * checkpoint / resume; the reference cannot serialise an env). Together with the generator
  * (rf_env_get/set_generator) and the renderer's RNG states (rf_rng_export/import) this is
  * everything a resumed run needs to continue bit-identically. h_states float32 [n, 2],
- * h_old_obs float32 [n, 4] (DeltaObserver), h_node_state uint32 [rf_env_node_rows(env), n]
+ * h_old_obs float32 [n, rf_env_delta_width(env)] (the DeltaObservers' previous values),
+ * h_node_state uint32 [rf_env_node_rows(env), n]
  * (the enders' counters / windows and the rewarders' previous values, raw bits). Export
  * skips NULL pointers; import needs all of them and stands in for a reset. */
 int rf_env_node_rows(const rf_env *env);
+int rf_env_delta_width(const rf_env *env);
 int rf_env_export(rf_env *env, float *h_states, float *h_old_obs, uint32_t *h_node_state);
 int rf_env_import(rf_env *env, const float *h_states, const float *h_old_obs, const uint32_t *h_node_state);
 

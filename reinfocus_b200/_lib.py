@@ -19,7 +19,7 @@ RF_ERR_CUDA = -2
 RF_ERR_NOMEM = -3
 RF_ERR_NO_SCENE = -4
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH, SELFTEST_CONST_DIV = 0, 1, 2, 3
 OPT_FORCE_GENERIC = 0
@@ -32,7 +32,11 @@ ENV_DISCRETE_MOVE, ENV_CONTINUOUS_JUMP, ENV_CONTINUOUS_MOVE, ENV_DISCRETE_JUMP =
  ENV_ENDER_AND, ENV_ENDER_OR) = range(7)
 (ENV_REWARD_DELTA, ENV_REWARD_DISTANCE, ENV_REWARD_OBSERVATION, ENV_REWARD_ON_TARGET, ENV_REWARD_STOPPED,
  ENV_REWARD_ADD, ENV_REWARD_MUL) = range(7)
-ENV_MAX_NODES = 8
+ENV_OBS_ELEMENT, ENV_OBS_FOCUS, ENV_OBS_DELTA, ENV_OBS_NORMALIZED = range(4)
+ENV_MAX_NODES = 24
+ENV_MAX_OBS_NODES = 16
+ENV_MAX_OBS_DIM = 16
+ENV_MAX_OBS_VALUES = 32
 ENV_MAX_WINDOW = 16
 ENV_ACTIONS_INT32, ENV_ACTIONS_INT64, ENV_ACTIONS_FLOAT32 = 0, 1, 2
 
@@ -67,6 +71,13 @@ class EnvReward(ctypes.Structure):
                 ("d0", ctypes.c_double), ("d1", ctypes.c_double)]
 
 
+class EnvObserver(ctypes.Structure):
+    """rf_env_observer."""
+
+    _fields_ = [("kind", ctypes.c_int), ("arg", ctypes.c_int), ("flag", ctypes.c_int),
+                ("offset", ctypes.c_int)]
+
+
 class EnvConfig(ctypes.Structure):
     """rf_env_config."""
 
@@ -82,11 +93,10 @@ class EnvConfig(ctypes.Structure):
         ("move_speed", ctypes.c_float),
         ("jumps", ctypes.c_float * 32),
         ("n_enders", ctypes.c_int), ("n_rewards", ctypes.c_int),
-        ("enders", EnvEnder * 8),
-        ("rewards", EnvReward * 8),
-        ("n_base", ctypes.c_int), ("base_index", ctypes.c_int * 4),
-        ("obs_delta", ctypes.c_int), ("obs_original", ctypes.c_int), ("obs_normalized", ctypes.c_int),
-        ("obs_mid", ctypes.c_float * 8), ("obs_scale", ctypes.c_float * 8),
+        ("enders", EnvEnder * ENV_MAX_NODES),
+        ("rewards", EnvReward * ENV_MAX_NODES),
+        ("n_observers", ctypes.c_int), ("observers", EnvObserver * ENV_MAX_OBS_NODES),
+        ("obs_mid", ctypes.c_float * ENV_MAX_OBS_VALUES), ("obs_scale", ctypes.c_float * ENV_MAX_OBS_VALUES),
         ("init_options", ctypes.c_int * 2),
         ("init_low", (ctypes.c_double * 4) * 2), ("init_high", (ctypes.c_double * 4) * 2),
         ("packing", ScenePacking),
@@ -140,6 +150,7 @@ _SIGNATURES = {
                                    ctypes.POINTER(ctypes.c_int), _vp]),
     "rf_env_node_rows": (ctypes.c_int, [_vp]),
     "rf_env_obs_dim": (ctypes.c_int, [_vp]),
+    "rf_env_delta_width": (ctypes.c_int, [_vp]),
     "rf_env_export": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "rf_env_import": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "rf_selftest": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int,
@@ -444,7 +455,9 @@ class DeviceEnv:
 
     def _layout(self):
         rows = int(self._lib.rf_env_node_rows(self._handle))
-        return (("states", numpy.float32, (self.num_envs, 2)), ("old_obs", numpy.float32, (self.num_envs, 4)),
+        delta_width = int(self._lib.rf_env_delta_width(self._handle))
+        return (("states", numpy.float32, (self.num_envs, 2)),
+                ("old_obs", numpy.float32, (self.num_envs, delta_width)),
                 ("node_state", numpy.uint32, (rows, self.num_envs)))
 
     def export(self) -> dict:

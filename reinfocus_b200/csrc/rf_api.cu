@@ -19,7 +19,7 @@
 #include "rf_tracer.cuh"
 #include "rf_tracer_mp.cuh"
 
-#define RF_ABI_VERSION 8
+#define RF_ABI_VERSION 9
 
 namespace {
 
@@ -58,6 +58,13 @@ struct rf_ctx {
     double *d_focus = nullptr;
     int cap_focus_out = 0;
     unsigned long long *d_misc = nullptr;  // small scratch (selftests)
+
+    // general-scene path (rf_render_generic): scene scratch, pristine seed states + working copy
+    uint8_t *d_generic_scene = nullptr;
+    size_t cap_generic_scene = 0;
+    rf::RngState *d_generic_pristine = nullptr, *d_generic_states = nullptr;
+    int64_t cap_generic_states = 0;
+    uint64_t generic_seed = 0;
 
     bool force_generic = false;  // RF_OPT_FORCE_GENERIC
     int trace_contexts = -1;     // RF_OPT_TRACE_CONTEXTS: pixels per thread of the default-camera kernel (-1 = by batch size)
@@ -125,6 +132,7 @@ int grow(rf_ctx *ctx, void **ptr, size_t bytes) {
 int ensure_focus_scratch(rf_ctx *ctx, int n, cudaStream_t stream) {
     if (n <= ctx->cap_focus) return RF_OK;
     const int cap = std::max(n, 64);
+    ctx->cap_focus = 0;
     if (int rc = grow(ctx, (void **)&ctx->d_accum, sizeof(unsigned long long) * 2 * cap)) return rc;
     if (int rc = grow(ctx, (void **)&ctx->d_tickets, sizeof(unsigned int) * cap)) return rc;
     RF_CUDA(ctx, cudaMemsetAsync(ctx->d_accum, 0, sizeof(unsigned long long) * 2 * cap, stream));
@@ -240,11 +248,14 @@ int launch_focus_packed(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, 
     // the grid should fill the resident warps and come in enough waves that the last one's
     // tail is small. Cost model, checked against measurements from 1 to 4096 envs:
     // (1 + 4 / band) * (w >= 1 ? ceil(w) / w : 1 / w) with w = tiles / resident warps.
+    // A tile's sums of the Laplacian and of its square stay in 32 bits until the atomics:
+    // 120 columns x 255^2 x rows < 2^32 needs rows <= 550, hence the cap.
     const double resident = (double)ctx->prop.multiProcessorCount * 32;
-    int band = H;
+    int band = std::min(H, rf::kPackedMaxBand);
     double best = 1e300;
     for (int k = 1; k <= std::max(1, H / 4); ++k) {
         const int rows = (H + k - 1) / k;
+        if (rows > rf::kPackedMaxBand) continue;
         const double w = (double)n * p.segs * ((H + rows - 1) / rows) / resident;
         const double fill = w >= 1.0 ? std::ceil(w) / w : 1.0 / w;
         const double cost = (1.0 + 4.0 / rows) * fill;
@@ -411,6 +422,9 @@ int rf_destroy(rf_ctx *ctx) {
     cudaFree(ctx->d_gray);
     cudaFree(ctx->d_focus);
     cudaFree(ctx->d_misc);
+    cudaFree(ctx->d_generic_scene);
+    cudaFree(ctx->d_generic_pristine);
+    cudaFree(ctx->d_generic_states);
     delete ctx;
     return RF_OK;
 }
@@ -516,6 +530,7 @@ int rf_set_world(rf_ctx *ctx, int n, const float *h_world, void *stream) {
     DeviceGuard guard(ctx->device);
     if (n > ctx->cap_world) {
         RF_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+        ctx->cap_world = 0;  // a failed allocation must not leave a stale capacity behind
         if (int rc = grow(ctx, (void **)&ctx->d_world, sizeof(float) * 2 * (size_t)n)) return rc;
         ctx->cap_world = n;
     }
@@ -534,6 +549,7 @@ int rf_set_cameras(rf_ctx *ctx, int n, const float *h_cam_dyn, const float origi
     DeviceGuard guard(ctx->device);
     if (n > ctx->cap_cam) {
         RF_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+        ctx->cap_cam = 0;
         if (int rc = grow(ctx, (void **)&ctx->d_cam_dyn, sizeof(float) * 9 * (size_t)n)) return rc;
         ctx->cap_cam = n;
     }
@@ -587,32 +603,44 @@ int rf_render_generic(rf_ctx *ctx, int n, int H, int W, int spp, int max_shapes,
     const size_t bytes_types = sizeof(int) * (size_t)n * max_shapes;
     const size_t bytes_sizes = sizeof(int) * (size_t)n;
     const size_t bytes_cams = sizeof(double) * (size_t)n * rf::kCameraFields;
-    // one scratch allocation: cameras | params | types | sizes | states (fresh every call,
-    // reference render.py:115)
+    // scratch kept by the context: cameras | params | types | sizes, and two state arrays.
+    // The reference seeds fresh states on every call (render.py:115); states of a smaller
+    // batch are a prefix of those of a larger one, so one pristine copy per (seed, largest
+    // batch so far) is kept and each call starts from a device-to-device copy of its prefix.
     const size_t off_params = bytes_cams;
     const size_t off_types = off_params + bytes_params;
     const size_t off_sizes = off_types + bytes_types;
-    const size_t off_states = (off_sizes + bytes_sizes + 15) & ~(size_t)15;
-    uint8_t *scratch = nullptr;
-    RF_CUDA(ctx, cudaMalloc((void **)&scratch, off_states + sizeof(rf::RngState) * (size_t)total));
-    auto release = [&](int code) {
-        cudaStreamSynchronize(s);
-        cudaFree(scratch);
-        return code;
-    };
-    if (cudaMemcpyAsync(scratch, h_cameras, bytes_cams, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemcpyAsync(scratch + off_params, h_shape_params, bytes_params, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemcpyAsync(scratch + off_types, h_shape_types, bytes_types, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemcpyAsync(scratch + off_sizes, h_env_sizes, bytes_sizes, cudaMemcpyHostToDevice, s) != cudaSuccess)
-        return release(fail(ctx, RF_ERR_CUDA, "rf_render_generic: upload failed"));
-    rf::RngState *states = reinterpret_cast<rf::RngState *>(scratch + off_states);
-    if (int rc = rng_init_into(ctx, states, total, seed, s)) return release(rc);
+    const size_t scene_bytes = off_sizes + bytes_sizes;
+    if (scene_bytes > ctx->cap_generic_scene) {
+        RF_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->cap_generic_scene = 0;
+        if (int rc = grow(ctx, (void **)&ctx->d_generic_scene, scene_bytes)) return rc;
+        ctx->cap_generic_scene = scene_bytes;
+    }
+    if (total > ctx->cap_generic_states || seed != ctx->generic_seed) {
+        RF_CUDA(ctx, cudaStreamSynchronize(s));
+        if (total > ctx->cap_generic_states) {
+            ctx->cap_generic_states = 0;
+            if (int rc = grow(ctx, (void **)&ctx->d_generic_pristine, sizeof(rf::RngState) * (size_t)total)) return rc;
+            if (int rc = grow(ctx, (void **)&ctx->d_generic_states, sizeof(rf::RngState) * (size_t)total)) return rc;
+            ctx->cap_generic_states = total;
+        }
+        if (int rc = rng_init_into(ctx, ctx->d_generic_pristine, ctx->cap_generic_states, seed, s)) return rc;
+        ctx->generic_seed = seed;
+    }
+    uint8_t *scratch = ctx->d_generic_scene;
+    RF_CUDA(ctx, cudaMemcpyAsync(scratch, h_cameras, bytes_cams, cudaMemcpyHostToDevice, s));
+    RF_CUDA(ctx, cudaMemcpyAsync(scratch + off_params, h_shape_params, bytes_params, cudaMemcpyHostToDevice, s));
+    RF_CUDA(ctx, cudaMemcpyAsync(scratch + off_types, h_shape_types, bytes_types, cudaMemcpyHostToDevice, s));
+    RF_CUDA(ctx, cudaMemcpyAsync(scratch + off_sizes, h_env_sizes, bytes_sizes, cudaMemcpyHostToDevice, s));
+    RF_CUDA(ctx, cudaMemcpyAsync(ctx->d_generic_states, ctx->d_generic_pristine, sizeof(rf::RngState) * (size_t)total,
+                                 cudaMemcpyDeviceToDevice, s));
     rf::GenericParams p{};
     p.cameras = reinterpret_cast<const double *>(scratch);
     p.shape_params = reinterpret_cast<const float *>(scratch + off_params);
     p.shape_types = reinterpret_cast<const int *>(scratch + off_types);
     p.env_sizes = reinterpret_cast<const int *>(scratch + off_sizes);
-    p.states = states;
+    p.states = ctx->d_generic_states;
     p.rgb = d_rgb;
     p.scale = (float)(255.0 / (double)spp);
     p.n = n;
@@ -622,11 +650,11 @@ int rf_render_generic(rf_ctx *ctx, int n, int H, int W, int spp, int max_shapes,
     p.max_shapes = max_shapes;
     p.total = total;
     const int64_t blocks = (total + rf::kTraceThreads - 1) / rf::kTraceThreads;
-    if (blocks > 0x7fffffffLL) return release(fail(ctx, RF_ERR_INVALID, "render batch too large"));
+    if (blocks > 0x7fffffffLL) return fail(ctx, RF_ERR_INVALID, "render batch too large");
     rf::trace_generic_kernel<<<(unsigned)blocks, rf::kTraceThreads, 0, s>>>(p);
     ctx->launches++;
-    if (cudaGetLastError() != cudaSuccess) return release(fail(ctx, RF_ERR_CUDA, "generic tracer launch failed"));
-    return release(RF_OK);
+    RF_CUDA(ctx, cudaGetLastError());
+    return RF_OK;
 }
 
 // -------------------------------------------------------------------------------- focus
@@ -653,11 +681,13 @@ static int ensure_step_scratch(rf_ctx *ctx, int n, int H, cudaStream_t stream) {
     const int64_t need = (int64_t)n * H * H;
     if (need > ctx->cap_gray) {
         RF_CUDA(ctx, cudaStreamSynchronize(stream));
+        ctx->cap_gray = 0;
         if (int rc = grow(ctx, (void **)&ctx->d_gray, (size_t)need)) return rc;
         ctx->cap_gray = need;
     }
     if (n > ctx->cap_focus_out) {
         RF_CUDA(ctx, cudaStreamSynchronize(stream));
+        ctx->cap_focus_out = 0;
         if (int rc = grow(ctx, (void **)&ctx->d_focus, sizeof(double) * (size_t)n)) return rc;
         ctx->cap_focus_out = n;
     }
@@ -705,11 +735,13 @@ int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float 
     cudaStream_t s = (cudaStream_t)stream;
     if (n > ctx->cap_world) {
         RF_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->cap_world = 0;
         if (int rc = grow(ctx, (void **)&ctx->d_world, sizeof(float) * 2 * (size_t)n)) return rc;
         ctx->cap_world = n;
     }
     if (n > ctx->cap_cam) {
         RF_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->cap_cam = 0;
         if (int rc = grow(ctx, (void **)&ctx->d_cam_dyn, sizeof(float) * 9 * (size_t)n)) return rc;
         ctx->cap_cam = n;
     }
@@ -799,27 +831,57 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
     p.limit_hi = c->limits[1];
     p.jump_span = c->jump_span;
     p.jump_threshold = c->jump_threshold;
-    int focus_observers = 0;
-    bool observer_ok = c->n_base >= 1 && c->n_base <= rf::kEnvMaxBase;
-    for (int b = 0; observer_ok && b < c->n_base; ++b) {
-        observer_ok = c->base_index[b] >= -1 && c->base_index[b] <= 1;
-        focus_observers += c->base_index[b] < 0;
-        p.base_index[b] = c->base_index[b];
-    }
-    if (!observer_ok || focus_observers != 1) {
-        delete env;
-        return fail(ctx, RF_ERR_INVALID,
-                    "rf_env_create: the observer needs 1..%d base observers, exactly one of them the focus value",
-                    rf::kEnvMaxBase);
-    }
-    p.n_base = c->n_base;
-    p.obs_delta = c->obs_delta != 0;
-    p.obs_original = p.obs_delta && c->obs_original != 0;
-    p.obs_normalized = c->obs_normalized != 0;
-    p.obs_dim = p.n_base * (p.obs_original ? 2 : 1);
-    for (int i = 0; i < 2 * rf::kEnvMaxBase; ++i) {
-        p.obs_mid[i] = c->obs_mid[i];
-        p.obs_scale[i] = c->obs_scale[i];
+    // the observer program: well-formed postfix, one FocusObserver, widths within bounds
+    {
+        int widths[rf::kEnvMaxObsNodes];
+        int top = 0, used = 0, focus_observers = 0, delta_width = 0, normalized = 0;
+        bool ok = c->n_observers >= 1 && c->n_observers <= rf::kEnvMaxObsNodes;
+        for (int k = 0; ok && k < c->n_observers; ++k) {
+            const rf_env_observer &src = c->observers[k];
+            rf::ObsNode &node = p.obs_nodes[k];
+            node = rf::ObsNode{src.kind, src.arg, src.flag != 0, 0};
+            if (src.kind == RF_ENV_OBS_ELEMENT || src.kind == RF_ENV_OBS_FOCUS) {
+                ok = src.kind == RF_ENV_OBS_FOCUS || (src.arg >= 0 && src.arg <= 1);
+                focus_observers += src.kind == RF_ENV_OBS_FOCUS;
+                widths[top++] = 1;
+                ok = ok && ++used <= rf::kEnvMaxObsStack;
+            } else if (src.kind == RF_ENV_OBS_DELTA || src.kind == RF_ENV_OBS_NORMALIZED) {
+                ok = src.arg >= 1 && src.arg <= top;
+                int width = 0;
+                for (int j = 0; ok && j < src.arg; ++j) width += widths[--top];
+                if (!ok) break;
+                if (src.kind == RF_ENV_OBS_DELTA) {
+                    node.offset = delta_width;
+                    delta_width += width;
+                    if (node.flag) {
+                        used += width;
+                        width *= 2;
+                    }
+                } else {
+                    node.offset = src.offset;
+                    ok = src.offset >= 0 && src.offset + width <= rf::kEnvMaxObsStack;
+                    normalized = std::max(normalized, src.offset + width);
+                }
+                ok = ok && used <= rf::kEnvMaxObsStack;
+                widths[top++] = width;
+            } else {
+                ok = false;
+            }
+        }
+        if (!ok || top != 1 || focus_observers != 1 || widths[0] > rf::kEnvMaxObsDim) {
+            delete env;
+            return fail(ctx, RF_ERR_INVALID,
+                        "rf_env_create: the observer program must reduce to one vector of at most %d columns "
+                        "with exactly one FocusObserver",
+                        rf::kEnvMaxObsDim);
+        }
+        p.n_obs = c->n_observers;
+        p.obs_dim = widths[0];
+        p.delta_width = delta_width;
+        for (int i = 0; i < rf::kEnvMaxObsStack; ++i) {
+            p.obs_mid[i] = i < normalized ? c->obs_mid[i] : 0.0f;
+            p.obs_scale[i] = i < normalized ? c->obs_scale[i] : 1.0f;
+        }
     }
     // the programs: check that they are well-formed postfix expressions over state indices
     // 0 / 1, and give every node its per-env state rows
@@ -889,7 +951,7 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
     const bool ok = alloc((void **)&a.states, sizeof(float) * 2 * n) &&
                     alloc((void **)&a.new_states, sizeof(float) * 2 * n) &&
                     alloc((void **)&a.reset_rank, sizeof(int) * n) &&
-                    alloc((void **)&a.old_obs, sizeof(float) * rf::kEnvMaxBase * n) &&
+                    alloc((void **)&a.old_obs, sizeof(float) * (size_t)std::max(p.delta_width, 1) * n) &&
                     alloc((void **)&a.node_state, sizeof(uint32_t) * n * (size_t)env->node_rows) &&
                     alloc((void **)&a.generator, sizeof(uint64_t) * 6) &&
                     alloc((void **)&a.counters, sizeof(int) * 2) &&
@@ -902,7 +964,10 @@ int rf_env_create(rf_ctx *ctx, const rf_env_config *c, rf_env **out) {
         rf_env_destroy(env);
         return fail(ctx, RF_ERR_NOMEM, "rf_env_create: allocation failed: %s", cudaGetErrorString(err));
     }
-    RF_CUDA(ctx, cudaDeviceSynchronize());
+    if (const cudaError_t err = cudaDeviceSynchronize(); err != cudaSuccess) {
+        rf_env_destroy(env);
+        return fail(ctx, RF_ERR_CUDA, "rf_env_create: %s", cudaGetErrorString(err));
+    }
     *out = env;
     return RF_OK;
 }
@@ -1031,7 +1096,7 @@ int env_copy_arrays(rf_env *env, bool to_host, float *h_states, float *h_old_obs
         size_t bytes;
     } items[] = {
         {h_states, a.states, sizeof(float) * 2 * n},
-        {h_old_obs, a.old_obs, sizeof(float) * rf::kEnvMaxBase * n},
+        {h_old_obs, a.old_obs, sizeof(float) * (size_t)std::max(env->params.delta_width, 1) * n},
         {h_node_state, a.node_state, sizeof(uint32_t) * n * (size_t)env->node_rows},
     };
     for (const Item &item : items) {
@@ -1049,6 +1114,8 @@ int env_copy_arrays(rf_env *env, bool to_host, float *h_states, float *h_old_obs
 int rf_env_node_rows(const rf_env *env) { return env ? env->node_rows : 0; }
 
 int rf_env_obs_dim(const rf_env *env) { return env ? env->params.obs_dim : 0; }
+
+int rf_env_delta_width(const rf_env *env) { return env ? std::max(env->params.delta_width, 1) : 0; }
 
 int rf_env_export(rf_env *env, float *h_states, float *h_old_obs, uint32_t *h_node_state) {
     if (!env) return fail(nullptr, RF_ERR_INVALID, "rf_env_export: env is NULL");

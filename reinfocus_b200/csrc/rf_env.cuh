@@ -21,9 +21,12 @@ enum { kEnderTimeLimit = 0, kEnderDiverging = 1, kEnderOnTarget = 2, kEnderStopp
        kEnderAnd = 5, kEnderOr = 6 };
 enum { kRewardDelta = 0, kRewardDistance = 1, kRewardObservation = 2, kRewardOnTarget = 3, kRewardStopped = 4,
        kRewardAdd = 5, kRewardMul = 6 };
+enum { kObsElement = 0, kObsFocus = 1, kObsDelta = 2, kObsNormalized = 3 };
 constexpr int kEnvMaxMoves = 32;
-constexpr int kEnvMaxNodes = 8;
-constexpr int kEnvMaxBase = 4;
+constexpr int kEnvMaxNodes = 24;     // nodes of the ender / rewarder programs
+constexpr int kEnvMaxObsNodes = 16;  // nodes of the observer program
+constexpr int kEnvMaxObsDim = 16;    // columns of an observation
+constexpr int kEnvMaxObsStack = 32;  // float32 values alive while the observer program runs
 constexpr int kEnvMaxRanges = 4;
 constexpr int kEnvMaxWindow = 16;  // StoppedEnder: early_end_steps + 1 positions
 constexpr int kEnvPreThreads = 1024;
@@ -44,6 +47,16 @@ struct RewardNode {
     double d0, d1;     // Distance: low; OnTarget: off, delta; Stopped: reward
 };
 
+// One node of the observer tree, in postfix order (reference state_observer.py:103-517).
+// ELEMENT pushes a state element, FOCUS the focus value; DELTA / NORMALIZED consume the last
+// `arg` vectors side by side (the hstack of WrapperObserver.wrapped_observations).
+struct ObsNode {
+    int kind;
+    int arg;     // ELEMENT: state index; DELTA / NORMALIZED: number of child observers
+    int flag;    // DELTA: include_original
+    int offset;  // DELTA: first of its old-observation columns; NORMALIZED: first mid / scale column
+};
+
 struct EnvParams {
     int n;
     int transformer;             // kEnvDiscreteMove ... kEnvDiscreteJump
@@ -57,12 +70,13 @@ struct EnvParams {
     int n_enders, n_rewards;
     EnderNode enders[kEnvMaxNodes];
     RewardNode rewards[kEnvMaxNodes];
-    // observer: n_base base observers side by side (a state element, or the focus value for
-    // index -1), optionally under a DeltaObserver (changes, preceded by the values themselves
-    // with include_original), optionally under a NormalizedObserver
-    int n_base, base_index[kEnvMaxBase];
-    int obs_delta, obs_original, obs_normalized, obs_dim;
-    float obs_mid[2 * kEnvMaxBase], obs_scale[2 * kEnvMaxBase];  // NormalizedObserver
+    // observer: any tree of IndexedElementObservers and one FocusObserver under DeltaObservers
+    // and NormalizedObservers, as a postfix program
+    int n_obs;
+    ObsNode obs_nodes[kEnvMaxObsNodes];
+    int obs_dim;      // columns the root leaves
+    int delta_width;  // old-observation columns per env, over all DeltaObservers
+    float obs_mid[kEnvMaxObsStack], obs_scale[kEnvMaxObsStack];  // NormalizedObservers, by their offsets
     // RangedInitializer: per state element up to kEnvMaxRanges (low, high - low) pairs; with
     // more than one, Generator.choice picks the pair before Generator.uniform draws in it
     int init_options[2];
@@ -73,7 +87,7 @@ struct EnvArrays {
     float *states;        // [n, 2]  target, focus plane
     float *new_states;    // [n, 2]  first states of restarted episodes, by reset rank
     int *reset_rank;      // [n]     position among this step's restarted envs, -1 if none
-    float *old_obs;       // [n, kEnvMaxBase]  DeltaObserver: the base observers' previous values
+    float *old_obs;       // [n, delta_width]  DeltaObservers: their children's previous values
     uint32_t *node_state; // [rows, n] per-env state of the ender / rewarder nodes (int or float bits)
     uint64_t *generator;  // [6]     PCG64DXSM state hi, lo, increment hi, lo, has_uint32, uinteger
     int *counters;        // [2]     number of restarted envs, invalid-action flag
@@ -168,30 +182,46 @@ __device__ inline float clip_f32(float x, float lo, float hi) {
 
 __device__ inline float env_gap(float target, float plane) { return fabsf(__fsub_rn(target, plane)); }
 
-// observer.observe / observer.reset of one env: the wrapped observers' values side by side
-// (hstack casts the float64 focus value to float32), DeltaObserver's changes since the
-// previous step (zeros when the episode just started, reference state_observer.py:283-290),
-// NormalizedObserver's clip((values - mid) / scale, -1, 1)
+// observer.observe / observer.reset of one env: the observer tree as a postfix program over
+// a stack of float32 vectors that lie side by side in `out`. A wrapper takes its children's
+// vectors as one (hstack; the float64 focus value is cast to float32 there). DeltaObserver:
+// changes since the previous step - zeros when the episode just started (`fresh`, reference
+// state_observer.py:283-290) - after the values themselves with include_original;
+// NormalizedObserver: clip((values - mid) / scale, -1, 1). Leaves the root's vector in
+// out[0 .. obs_dim).
 __device__ inline void observe(const EnvParams &p, const EnvArrays &a, int env, const float *state, double focus,
                                bool fresh, float *out) {
-    float current[kEnvMaxBase];
-    for (int b = 0; b < p.n_base; ++b)
-        current[b] = p.base_index[b] < 0 ? __double2float_rn(focus) : state[p.base_index[b]];
-    int dim = 0;
-    if (!p.obs_delta) {
-        for (int b = 0; b < p.n_base; ++b) out[dim++] = current[b];
-    } else {
-        if (p.obs_original)
-            for (int b = 0; b < p.n_base; ++b) out[dim++] = current[b];
-        for (int b = 0; b < p.n_base; ++b) {
-            float &previous = a.old_obs[(size_t)kEnvMaxBase * env + b];
-            out[dim++] = fresh ? 0.0f : __fsub_rn(current[b], previous);
-            previous = current[b];
+    int widths[kEnvMaxObsNodes];
+    int top = 0, used = 0;
+    for (int k = 0; k < p.n_obs; ++k) {
+        const ObsNode &node = p.obs_nodes[k];
+        if (node.kind == kObsElement || node.kind == kObsFocus) {
+            out[used++] = node.kind == kObsFocus ? __double2float_rn(focus) : state[node.arg];
+            widths[top++] = 1;
+            continue;
         }
+        int width = 0;
+        for (int j = 0; j < node.arg; ++j) width += widths[--top];
+        float *values = out + used - width;
+        if (node.kind == kObsDelta) {
+            float *previous = a.old_obs + (size_t)p.delta_width * env + node.offset;
+            float *changes = node.flag ? values + width : values;
+            for (int c = 0; c < width; ++c) {
+                const float current = values[c];
+                changes[c] = fresh ? 0.0f : __fsub_rn(current, previous[c]);
+                previous[c] = current;
+            }
+            if (node.flag) {
+                used += width;
+                width *= 2;
+            }
+        } else {  // kObsNormalized
+            for (int c = 0; c < width; ++c)
+                values[c] = clip_f32(__fdiv_rn(__fsub_rn(values[c], p.obs_mid[node.offset + c]),
+                                               p.obs_scale[node.offset + c]), -1.0f, 1.0f);
+        }
+        widths[top++] = width;
     }
-    if (p.obs_normalized)
-        for (int c = 0; c < dim; ++c)
-            out[c] = clip_f32(__fdiv_rn(__fsub_rn(out[c], p.obs_mid[c]), p.obs_scale[c]), -1.0f, 1.0f);
 }
 
 // per-env state rows of the strategy nodes
@@ -490,7 +520,7 @@ __global__ void env_post_kernel(EnvParams p, EnvArrays a, const double *focus_ma
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
     const int rank = a.reset_rank[i];
-    float out[2 * kEnvMaxBase];
+    float out[kEnvMaxObsStack];
     if (!reset_all) {
         const float state[2] = {a.states[2 * i], a.states[2 * i + 1]};
         observe(p, a, i, state, focus_main[i], false, out);

@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(kFocusThreads) focus_kernel(const FocusParams 
 
 constexpr int kPackedWarps = 8;
 constexpr int kPackedCols = 120;  // productive columns per warp tile
+constexpr int kPackedMaxBand = 512;  // rows per warp tile: keeps the 32-bit tile sums from wrapping
 
 struct PackedFocusParams {
     const uint8_t *img;  // [n, H, W, channels]

@@ -13,11 +13,11 @@ What is understood (anything else raises ``NotImplementedError`` - use ``VectorE
 * state ``[target, focus plane]``;
 * any of the four transformers (discrete / continuous, move / jump) on the focus plane;
 * any ``&`` / ``|`` tree of ``TimeLimitEnder``, ``DivergingEnder``, ``OnTargetEnder``,
-  ``StoppedEnder``, ``EndlessEnder`` (up to 8 nodes);
-* observer: ``IndexedElementObserver``s and one ``FocusObserver`` side by side, optionally under
-  a ``DeltaObserver``, optionally under a ``NormalizedObserver``;
+  ``StoppedEnder``, ``EndlessEnder`` (up to 24 nodes);
+* observer: any tree of ``DeltaObserver``s and ``NormalizedObserver``s, nested in any order,
+  over ``IndexedElementObserver``s and one ``FocusObserver`` (up to 16 nodes and 16 columns);
 * any ``+`` / ``*`` tree of ``DeltaRewarder``, ``DistanceRewarder``, ``ObservationRewarder``,
-  ``OnTargetRewarder``, ``StoppedRewarder`` (up to 8 nodes), with NumPy's result types;
+  ``OnTargetRewarder``, ``StoppedRewarder`` (up to 24 nodes), with NumPy's result types;
 * initializer ``RangedInitializer`` (up to four ranges per element) on a PCG64DXSM generator.
 """
 
@@ -180,44 +180,67 @@ def _read_rewarder(rewarder, config: _lib.EnvConfig, columns: int = 4) -> bool:
 
 
 def _read_observer(observer, config: _lib.EnvConfig):
-    """IndexedElementObservers and exactly one FocusObserver side by side, optionally under a
-    DeltaObserver, optionally under a NormalizedObserver. Returns the FocusObserver's renderer."""
+    """Flattens the observer tree - DeltaObservers and NormalizedObservers, nested in any
+    order, over IndexedElementObservers and exactly one FocusObserver - into the postfix
+    program of rf_env_config. Returns the FocusObserver's renderer and the number of
+    observation columns."""
 
     # pylint: disable=protected-access
-    def is_base(node):
-        return isinstance(node, (state_observer.IndexedElementObserver, state_observer.FocusObserver))
+    program: list[_lib.EnvObserver] = []
+    focus_observers = []
+    normalized_columns = 0
+    alive_peak = 0
 
-    normalized = isinstance(observer, state_observer.NormalizedObserver)
-    inner = list(observer._observers) if normalized else [observer]
-    delta = None
-    if len(inner) == 1 and isinstance(inner[0], state_observer.DeltaObserver):
-        delta = inner[0]
-        bases = list(delta._observers)
-    elif normalized:
-        bases = inner
-    else:
-        _unsupported("observer")
-    if not bases or len(bases) > 4 or not all(is_base(base) for base in bases):
-        _unsupported("observer")
-    focus_observers = [base for base in bases if isinstance(base, state_observer.FocusObserver)]
+    def emit(node, alive: int) -> int:
+        """Appends `node`'s subtree; `alive`: values to the left that are still on the stack.
+        Returns the width of the vector the node leaves."""
+
+        nonlocal normalized_columns, alive_peak
+        if isinstance(node, state_observer.FocusObserver):
+            if (node._target_index, node._focus_plane_index) != (TARGET, FOCUS_PLANE):
+                _unsupported("observer (the FocusObserver must read [target, focus plane])")
+            focus_observers.append(node)
+            program.append(_lib.EnvObserver(_lib.ENV_OBS_FOCUS, 0, 0, 0))
+            alive_peak = max(alive_peak, alive + 1)
+            return 1
+        if isinstance(node, state_observer.IndexedElementObserver):
+            program.append(_lib.EnvObserver(_lib.ENV_OBS_ELEMENT, _state_index(node._element_index), 0, 0))
+            alive_peak = max(alive_peak, alive + 1)
+            return 1
+        if not isinstance(node, (state_observer.DeltaObserver, state_observer.NormalizedObserver)):
+            _unsupported("observer")
+        children = list(node._observers)
+        width = 0
+        for child in children:
+            width += emit(child, alive + width)
+        if isinstance(node, state_observer.DeltaObserver):
+            include = bool(node._include_original)
+            program.append(_lib.EnvObserver(_lib.ENV_OBS_DELTA, len(children), int(include), 0))
+            width *= 2 if include else 1
+        else:
+            assert node._mid.dtype == numpy.float32 and node._scale.dtype == numpy.float32
+            assert len(node._mid) == width == len(node._scale)
+            if normalized_columns + width > _lib.ENV_MAX_OBS_VALUES:
+                _unsupported(f"observer (more than {_lib.ENV_MAX_OBS_VALUES} normalised columns)")
+            for i in range(width):
+                config.obs_mid[normalized_columns + i] = float(node._mid[i])
+                config.obs_scale[normalized_columns + i] = float(node._scale[i])
+            program.append(_lib.EnvObserver(_lib.ENV_OBS_NORMALIZED, len(children), 0, normalized_columns))
+            normalized_columns += width
+        alive_peak = max(alive_peak, alive + width)
+        return width
+
+    columns = emit(observer, 0)
     if len(focus_observers) != 1:
         _unsupported("observer (exactly one FocusObserver renders per step)")
+    if len(program) > _lib.ENV_MAX_OBS_NODES:
+        _unsupported(f"observer (more than {_lib.ENV_MAX_OBS_NODES} nodes)")
+    if columns > _lib.ENV_MAX_OBS_DIM or alive_peak > _lib.ENV_MAX_OBS_VALUES:
+        _unsupported(f"observer (more than {_lib.ENV_MAX_OBS_DIM} columns)")
+    config.n_observers = len(program)
+    for i, node in enumerate(program):
+        config.observers[i] = node
     focus = focus_observers[0]
-    if (focus._target_index, focus._focus_plane_index) != (TARGET, FOCUS_PLANE):
-        _unsupported("observer (the FocusObserver must read [target, focus plane])")
-    config.n_base = len(bases)
-    for i, base in enumerate(bases):
-        config.base_index[i] = -1 if base is focus else _state_index(base._element_index)
-    config.obs_delta = int(delta is not None)
-    config.obs_original = int(delta is not None and delta._include_original)
-    config.obs_normalized = int(normalized)
-    columns = len(bases) * (2 if config.obs_original else 1)
-    if normalized:
-        assert observer._mid.dtype == numpy.float32 and observer._scale.dtype == numpy.float32
-        assert len(observer._mid) == columns
-        for i in range(columns):
-            config.obs_mid[i] = float(observer._mid[i])
-            config.obs_scale[i] = float(observer._scale[i])
     config.frame_height = int(focus._frame_height)
     return focus._renderer, columns
 

@@ -8,6 +8,8 @@ are exact."""
 
 import os
 
+import functools
+
 import numpy
 import pytest
 
@@ -165,7 +167,7 @@ def test_device_env_reads_strategy_trees_and_refuses_the_rest(modules):
                      _lib.ENV_ENDER_ENDLESS, _lib.ENV_ENDER_TIME_LIMIT, _lib.ENV_ENDER_OR, _lib.ENV_ENDER_AND]
     for ender in (enders.DivergingEnder(2, (0, 2), 0.1), enders.StoppedEnder(2, 1, 0.05, early_end_steps=16),
                   enders.OpEnder(time_limit, diverging, numpy.bitwise_xor),
-                  time_limit | time_limit | time_limit | time_limit | time_limit):
+                  functools.reduce(lambda a, b: a | b, [time_limit] * 13)):  # 25 nodes, the program holds 24
         with pytest.raises(NotImplementedError):
             dve._read_ender(ender, config)
 
@@ -222,3 +224,35 @@ def test_device_env_reads_strategy_trees_and_refuses_the_rest(modules):
     env, _, _ = gen_golden_env.sim_cases()["discrete_vector"](modules, focus_cls)
     with pytest.raises(NotImplementedError):  # the focus value must come from FocusObserver
         dve._read_observer(env._observer, config)
+
+    # nested observer wrappers flatten to a postfix program (children before parents)
+    observers = m.state_observer
+    observers.cached_focus_extrema.cache_clear()
+
+    class NoRenderer:  # pylint: disable=too-few-public-methods
+        """Stands in for a FastRenderer: reading the tree never renders."""
+
+    original = observers.cached_focus_extrema
+    observers.cached_focus_extrema = lambda ends, height: (50.0, 450.0)
+    try:
+        focus = observers.FocusObserver(2, 0, 1, (5.0, 10.0), NoRenderer(), 40)
+    finally:
+        observers.cached_focus_extrema = original
+    plane = observers.IndexedElementObserver(2, 1, 5.0, 10.0)
+    target = observers.IndexedElementObserver(2, 0, 5.0, 10.0)
+    nested = observers.NormalizedObserver([plane, observers.DeltaObserver(observers.NormalizedObserver(focus)),
+                                           observers.DeltaObserver([target], True)])
+    renderer, columns = dve._read_observer(nested, config)
+    assert isinstance(renderer, NoRenderer) and columns == 4 == nested.observation_space.shape[1]
+    program = [(o.kind, o.arg, o.flag, o.offset) for o in config.observers[:config.n_observers]]
+    assert program == [(_lib.ENV_OBS_ELEMENT, 1, 0, 0), (_lib.ENV_OBS_FOCUS, 0, 0, 0),
+                       (_lib.ENV_OBS_NORMALIZED, 1, 0, 0), (_lib.ENV_OBS_DELTA, 1, 0, 0),
+                       (_lib.ENV_OBS_ELEMENT, 0, 0, 0), (_lib.ENV_OBS_DELTA, 1, 1, 0),
+                       (_lib.ENV_OBS_NORMALIZED, 3, 0, 1)]
+    assert list(config.obs_mid[:1]) == [250.0] and list(config.obs_scale[:1]) == [200.0]
+    for bad in (observers.NormalizedObserver([plane, target]),                       # no FocusObserver
+                observers.DeltaObserver([focus, observers.NormalizedObserver(focus)]),  # two renders per step
+                observers.DeltaObserver([observers.DeltaObserver([plane, focus, target, plane, target], True)] * 2,
+                                        True)):                                       # 40 columns
+        with pytest.raises(NotImplementedError):
+            dve._read_observer(bad, config)

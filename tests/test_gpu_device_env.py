@@ -39,8 +39,20 @@ def _strategies(num_envs, renderer, seed, frame_height, kind="steps", max_steps=
             [plane, focus], True, numpy.array([5.0, numpy.nan])))
     elif observer_kind == "changes":  # three raw changes, neither the values nor a normalisation
         observer = state_observer.DeltaObserver([target, focus, plane])
-    else:  # "levels": normalised values without a DeltaObserver
+    elif observer_kind == "levels":  # normalised values without a DeltaObserver
         observer = state_observer.NormalizedObserver([focus, plane])
+    elif observer_kind == "nested":
+        # wrappers nested three deep and side by side: normalised [plane, change of the
+        # normalised focus value, [target, its change]]
+        observer = state_observer.NormalizedObserver([
+            plane,
+            state_observer.DeltaObserver(state_observer.NormalizedObserver(focus)),
+            state_observer.DeltaObserver([target], True)])
+    else:  # "stacked": a change of changes over a mix of wrappers and base observers
+        observer = state_observer.DeltaObserver([
+            state_observer.DeltaObserver([plane, focus], True, numpy.array([5.0, numpy.nan])),
+            state_observer.NormalizedObserver([target, plane]),
+            state_observer.IndexedElementObserver(num_envs, 0, *ENDS)], True)
     ender = episode_ender.DivergingEnder(num_envs, (0, 1), 0.125, early_end_steps=3)
     if max_steps:
         ender = episode_ender.TimeLimitEnder(num_envs, max_steps) | ender
@@ -208,11 +220,13 @@ def test_discrete_jump_device_env_equals_host_env(torch):
     assert _assert_same_rollout(host, device, actions) > 0
 
 
-@pytest.mark.parametrize("observer_kind,reward_column", [("changes", 1), ("levels", 0)])
-def test_device_env_with_other_observer_layouts(torch, observer_kind, reward_column):
+@pytest.mark.parametrize("observer_kind,reward_column,columns",
+                         [("changes", 1, 3), ("levels", 0, 2), ("nested", 1, 4), ("stacked", 1, 14)])
+def test_device_env_with_other_observer_layouts(torch, observer_kind, reward_column, columns):
     """Observer layouts beyond the example envs': a bare DeltaObserver over three base
-    observers (changes only, not normalised) and a NormalizedObserver without a DeltaObserver;
-    the ObservationRewarder reads the focus column of each."""
+    observers (changes only, not normalised), a NormalizedObserver without a DeltaObserver,
+    and wrappers nested inside one another (reference state_observer.py:103-164 allows any
+    nesting); the ObservationRewarder reads a focus column of each."""
 
     from reinfocus_b200.environments import device_vector_environment, episode_rewarder, vector_environment
     from reinfocus_b200.graphics import render
@@ -225,7 +239,7 @@ def test_device_env_with_other_observer_layouts(torch, observer_kind, reward_col
 
     host = build(vector_environment.VectorEnvironment, visualizer=None)
     device = build(device_vector_environment.DeviceVectorEnvironment)
-    assert device.reset()[0].shape == (6, 3 if observer_kind == "changes" else 2)
+    assert device.reset()[0].shape == (6, columns) == host.reset()[0].shape
     host, device = (build(vector_environment.VectorEnvironment, visualizer=None),
                     build(device_vector_environment.DeviceVectorEnvironment))
     actions = numpy.random.Generator(numpy.random.PCG64(12)).integers(0, 13, (50, 6))
@@ -246,6 +260,37 @@ def test_device_env_with_every_ender_and_rewarder_kind(torch, kind):
         actions = rng.integers(0, 13, (70, 7))
         actions[::4] = 6  # the zero move: stopped episodes
     assert _assert_same_rollout(host, device, actions) > 7
+
+
+def test_device_env_with_large_ender_and_rewarder_trees(torch):
+    """Strategy trees of 17 ender nodes and 21 rewarder nodes (the programs hold 24)."""
+
+    from reinfocus_b200.environments import (device_vector_environment, episode_ender, episode_rewarder,
+                                             vector_environment)
+    from reinfocus_b200.graphics import render
+
+    n = 5
+
+    def build(env_class, **extra):
+        parts = _strategies(n, render.FastRenderer(samples_per_pixel=5), 43, 36)
+        ender = episode_ender.TimeLimitEnder(n, 11)
+        for k in range(2):
+            ender = (ender | episode_ender.DivergingEnder(n, (0, 1), 0.05 * (k + 1), early_end_steps=2 + k)) & (
+                episode_ender.EndlessEnder(n) | episode_ender.OnTargetEnder(n, (0, 1), 0.3 + 0.1 * k, early_end_steps=2)
+                | episode_ender.StoppedEnder(n, 1, 0.04 * (k + 1), early_end_steps=2))
+        rewarder = episode_rewarder.ObservationRewarder(1)
+        for k in range(3):
+            rewarder = rewarder + episode_rewarder.DeltaRewarder(1, 0.5 + k) * episode_rewarder.DistanceRewarder(
+                (0, 1), 5.0, -1.0, 1.0 + k) + episode_rewarder.OnTargetRewarder((0, 1), 0.25 * (k + 1))
+        rewarder = rewarder + episode_rewarder.StoppedRewarder(1, 0.1, 2.0)
+        parts["ender"], parts["rewarder"] = ender, rewarder
+        return env_class(**parts, num_envs=n, **extra)
+
+    host = build(vector_environment.VectorEnvironment, visualizer=None)
+    device = build(device_vector_environment.DeviceVectorEnvironment)
+    actions = numpy.random.Generator(numpy.random.PCG64(21)).integers(0, 13, (60, n))
+    actions[::5] = 6
+    assert _assert_same_rollout(host, device, actions) > n
 
 
 def test_device_env_with_more_envs_than_one_scan_chunk(torch):

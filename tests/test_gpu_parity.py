@@ -533,6 +533,24 @@ def test_packed_focus_kernel_on_a_large_batch(torch):
     numpy.testing.assert_array_equal(got, oracle.focus_values_gray(gray))
 
 
+def test_packed_focus_kernel_tall_saturated_frames_in_a_large_batch(torch):
+    """Tall, high-contrast frames in a batch large enough that the launcher would give one
+    warp the whole column band: the tile sums of the squared Laplacian (120 x 255^2 per
+    row) pass 2^32 beyond 550 rows, so the band height is capped (kPackedMaxBand)."""
+
+    from reinfocus_b200 import vision
+
+    rng = numpy.random.default_rng(5)
+    height, width, distinct, copies = 2400, 120, 3, 1600
+    blocks = rng.integers(0, 2, size=(distinct, height // 3, width // 3), dtype=numpy.uint8) * 255
+    gray = numpy.repeat(numpy.repeat(blocks, 3, axis=1), 3, axis=2)  # 3 x 3 blocks survive the median
+    want = oracle.focus_values_gray(gray)
+    assert (want > 8000).all()  # mostly saturated Laplacian
+    batch = torch.from_numpy(gray).cuda().repeat(copies, 1, 1)
+    got = vision.focus_values_device(batch).cpu().numpy()
+    numpy.testing.assert_array_equal(got, numpy.tile(want, copies))
+
+
 def test_focus_planes_match_oracle(ctx, torch):
     rng = numpy.random.default_rng(3)
     gray = rng.integers(0, 256, size=(4, 37, 53), dtype=numpy.uint8)
