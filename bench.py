@@ -333,19 +333,32 @@ def run_ours(args):
     checksum = float(gathered.sum().item())
 
     # ------------------------------------------- per-kernel timing (tracer, focus stencil)
-    trace_ms, focus_ms = [], []
+    # (and, for N > 1, the obs gather and the host-side gap between steps: what the scaling
+    # run needs to name its limiter - max over ranks of each part)
+    trace_ms, focus_ms, gather_ms, step_wall_ms = [], [], [], []
+    barrier()
     for _ in range(min(args.steps, 3)):
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        t0 = time.perf_counter()
         e0.record()
         ctx.render(n_local, HEIGHT, HEIGHT, SPP, None, gray_dev.data_ptr())
         e1.record()
         ctx.focus(n_local, HEIGHT, HEIGHT, gray_dev.data_ptr(), 1, focus_dev.data_ptr())
         e2.record()
+        parallel.gather_observations(focus_dev, args.envs)
+        e3.record()
         torch.cuda.synchronize()
+        step_wall_ms.append((time.perf_counter() - t0) * 1e3)
         trace_ms.append(e0.elapsed_time(e1))
         focus_ms.append(e1.elapsed_time(e2))
+        gather_ms.append(e2.elapsed_time(e3))
     trace_ms = float(numpy.mean(trace_ms))
     focus_ms = float(numpy.mean(focus_ms))
+    breakdown = {"trace_ms": max_over_ranks(trace_ms), "focus_ms": max_over_ranks(focus_ms),
+                 "gather_ms": max_over_ranks(float(numpy.mean(gather_ms))),
+                 "step_wall_ms": max_over_ranks(float(numpy.mean(step_wall_ms))),
+                 "what": "max over ranks, one step at a time with a device sync after each: tracer launch, focus "
+                         "stencil, obs all-gather (includes waiting for the slowest rank), host wall clock"}
 
     # --------------------------------------------------- e2e: public API with host buffers
     for i in range(args.warmup):
@@ -496,6 +509,12 @@ def run_ours(args):
             "ms_per_step": device_env_loop_ms,
             "resets_per_step_rank0": device_resets / args.steps,
         },
+        "step_breakdown": dict(breakdown, timed_loop_ms_per_step=device_ms,
+                               blocks_per_gpu=n_local * ((HEIGHT * HEIGHT + 1791) // 1792),
+                               resident_blocks_per_gpu=info["sm_count"] * 4,
+                               note="the tracer runs 4 blocks of 1792 pixels x 100 samples per SM; a block lasts "
+                                    "trace_ms / waves, and the launch ends with up to one block time of partly "
+                                    "idle SMs - a fixed cost that weighs more the fewer envs a GPU owns"),
         "rng_init_s": rng_init_s,
         "device": {"sm_count": info["sm_count"], "cc": list(info["cc"])},
         "checksum": checksum,

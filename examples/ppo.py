@@ -241,6 +241,18 @@ class DeviceRolloutCollector:
         return data
 
 
+def minibatch_count(local_samples: int, batch_size: int, distributed: bool) -> int:
+    """Minibatches per epoch, identical on every rank: ceil(smallest shard / batch size)."""
+
+    smallest = local_samples
+    if distributed:
+        t = torch.tensor([local_samples], dtype=torch.int64,
+                         device="cuda" if torch.distributed.get_backend() == "nccl" else "cpu")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+        smallest = int(t.item())
+    return max(1, -(-smallest // batch_size))
+
+
 def ppo_update(policy: ActorCritic, optimizer, data, cfg: PPOConfig, device, max_minibatches=None):
     """Clipped-surrogate PPO epochs over one rollout; returns the last losses."""
 
@@ -248,11 +260,15 @@ def ppo_update(policy: ActorCritic, optimizer, data, cfg: PPOConfig, device, max
             if k in ("obs", "act", "logp", "adv", "ret")}
     size = flat["obs"].shape[0]
     distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
+    # every rank must run the same number of minibatches (each ends in a collective): shards
+    # can differ by one env (parallel.shard_bounds), so the count follows the smallest shard
+    # and a rank with a larger one spreads its samples over the same number of minibatches
+    n_batches = minibatch_count(size, cfg.batch_size, distributed)
     stats, batches = {}, 0
     for _ in range(cfg.n_epochs):
         order = torch.randperm(size, device=device)
-        for start in range(0, size, cfg.batch_size):
-            idx = order[start:start + cfg.batch_size]
+        for chunk in torch.tensor_split(order, n_batches):
+            idx = chunk
             dist, value = policy(flat["obs"][idx])
             adv = flat["adv"][idx]
             adv = (adv - adv.mean()) / (adv.std() + 1e-8)
@@ -264,9 +280,15 @@ def ppo_update(policy: ActorCritic, optimizer, data, cfg: PPOConfig, device, max
             optimizer.zero_grad()
             loss.backward()
             if distributed:
-                for param in policy.parameters():
-                    torch.distributed.all_reduce(param.grad)
-                    param.grad /= torch.distributed.get_world_size()
+                # one reduction over the flattened gradients, not one per parameter
+                grads = [param.grad for param in policy.parameters() if param.grad is not None]
+                flat_grads = torch.cat([g.reshape(-1) for g in grads])
+                torch.distributed.all_reduce(flat_grads)
+                flat_grads /= torch.distributed.get_world_size()
+                offset = 0
+                for g in grads:
+                    g.copy_(flat_grads[offset:offset + g.numel()].view_as(g))
+                    offset += g.numel()
             nn.utils.clip_grad_norm_(policy.parameters(), cfg.max_grad_norm)
             optimizer.step()
             stats = {name: float(term.detach()) for name, term in (("loss", loss), ("pg", pg_loss), ("vf", vf_loss), ("entropy", entropy))}

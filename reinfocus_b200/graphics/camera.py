@@ -75,6 +75,7 @@ class FastCameras(device_data.DeviceData):
         self._w = vector.norm_v3f(vector.sub_v3f(look_from, look_at))
         self._u = vector.norm_v3f(vector.cross_v3f(up, self._w))
         self._v = vector.cross_v3f(self._w, self._u)
+        self._constants = None
 
     @property
     def statics(self):
@@ -102,15 +103,16 @@ class FastCameras(device_data.DeviceData):
         #   horizontal = u * (2*hw*f),  vertical = v * (2*hh*f)
         # Python floats are weak under NumPy 2, so hw, hh, 2*hw, 2*hh enter as float32.
         f32 = numpy.float32
-        u = numpy.asarray(self._u, dtype=f32)
-        v = numpy.asarray(self._v, dtype=f32)
-        w = numpy.asarray(self._w, dtype=f32)
-        origin = numpy.asarray(self._look_from, dtype=f32)
+        if self._constants is None:  # the per-camera constants, converted once
+            self._constants = tuple(numpy.asarray(x, dtype=f32)[None, :]
+                                    for x in (self._u, self._v, self._w, self._look_from)) + (
+                f32(self._half_width), f32(self._half_height),
+                f32(2.0 * self._half_width), f32(2.0 * self._half_height))
+        u, v, w, origin, half_width, half_height, full_width, full_height = self._constants
         f = data[:, None]
-        total = (u[None, :] * (f32(self._half_width) * f)
-                 + v[None, :] * (f32(self._half_height) * f)) + w[None, :] * f
+        total = (u * (half_width * f) + v * (half_height * f)) + w * f
         packed = numpy.empty((len(data), 3, 3), dtype=f32)
-        packed[:, 0, :] = origin[None, :] - total
-        packed[:, 1, :] = u[None, :] * (f32(2.0 * self._half_width) * f)
-        packed[:, 2, :] = v[None, :] * (f32(2.0 * self._half_height) * f)
+        packed[:, 0, :] = origin - total
+        packed[:, 1, :] = u * (full_width * f)
+        packed[:, 2, :] = v * (full_height * f)
         return packed
