@@ -469,7 +469,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {
-            "kernel": "rf::trace_mc_kernel" if ctx.last_trace_kernel() > 1 else "rf::trace_kernel",
+            "kernel": "rf::trace_mp_kernel" if ctx.last_trace_kernel() > 1 else "rf::trace_kernel",
             "pixels_per_thread": max(ctx.last_trace_kernel(), 1), "bound": "fp32",
             "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / fp32_peak if fp32_peak else None,
@@ -484,6 +484,9 @@ def run_ours(args):
             # what actually binds this kernel: warp instructions issued per second
             # against 4 schedulers x 1 instruction / clock / SM; instruction count from ncu
             "issue": issue_view(traffic, n_local, trace_ms, info["sm_count"], clocks.summary()),
+            # ... and the pipe that binds it: LOP3 / SHF / IADD3 of xoroshiro128+ on the ALU pipe
+            # (16 lanes per scheduler: one warp instruction per 2 clocks)
+            "alu": alu_view(traffic, n_local, trace_ms, info["sm_count"], clocks.summary()),
             "hbm": {"achieved": n_local * HEIGHT * HEIGHT * 33 / (trace_ms * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s"},
         },
@@ -552,6 +555,20 @@ def issue_view(traffic, n_local, trace_ms, sm_count, clock_summary):
             "source": "static ncu capture: smsp__inst_executed.sum per env at 256 envs "
                       "(profiles/ncu_traffic.json); peak = SMs x 4 schedulers x sampled SM clock",
             "ncu_pct": traffic.get("trace_kernel_ncu_pct")}
+
+
+def alu_view(traffic, n_local, trace_ms, sm_count, clock_summary):
+    per_env = traffic.get("trace_kernel_alu_warp_inst_per_env")
+    mhz = clock_summary.get("sm_mhz") or clock_summary.get("sm_max_mhz")
+    if not per_env or not mhz:
+        return None
+    achieved = per_env * n_local / (trace_ms * 1e-3) / 1e9
+    peak = sm_count * 4 * mhz * 1e6 / 2 / 1e9
+    return {"warp_inst_per_launch": per_env * n_local, "achieved": achieved, "peak": peak,
+            "unit": "G ALU-pipe warp-inst/s", "frac": achieved / peak,
+            "source": "static ncu capture: executed LOP3 / SHF / IADD3 / ISETP / FSETP ... per env at 256 envs "
+                      "(profiles/r02/mp8_opcode_mix.txt); peak = SMs x 4 schedulers x sampled SM clock / 2 "
+                      "(measured: tools/pipe_microbench.cu, 2.0 clocks per warp instruction)"}
 
 
 _RESULT_STREAM = None
