@@ -325,12 +325,13 @@ int rf_selftest(rf_ctx *ctx, int which, int arg, int64_t *mismatches, void *stre
 /* Options. RF_OPT_FORCE_GENERIC = 1 makes rf_render use the literal any-camera kernel and
  * rf_focus the general staged kernel even when the specialised ones apply (A/B parity
  * tests). RF_OPT_TRACE_CONTEXTS = -1 (default), 0 or 2..8: pixels per thread of the
- * default-camera tracer (0 = the one-pixel-per-thread kernel, -1 = 7 once the batch fills
- * every SM a few times over, else 0); every setting produces the same bytes. */
+ * default-camera tracer (0 = the one-pixel-per-thread kernel, -1 = by batch size: 0 for a
+ * few envs, 4 once the batch fills every SM, 8 once it fills the GPU a few times over);
+ * every setting produces the same bytes. */
 enum { RF_OPT_FORCE_GENERIC = 0, RF_OPT_TRACE_CONTEXTS = 1 };
 int rf_set_option(rf_ctx *ctx, int option, int value);
 /* Introspection. RF_INFO_LAST_TRACE_KERNEL: 1 if the last rf_render used the specialised
- * one-pixel-per-thread kernel, 2..8 for the multi-context kernel with that many pixels
+ * one-pixel-per-thread kernel, 2..8 for the multi-pixel kernel with that many pixels
  * per thread, 0 for the generic one, -1 before any render. RF_INFO_LAST_FOCUS_KERNEL: 1 if the
  * last rf_focus used the packed kernel, 0 for the staged one. */
 enum { RF_INFO_LAST_TRACE_KERNEL = 0, RF_INFO_LAST_FOCUS_KERNEL = 1 };

@@ -189,12 +189,14 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
                       ctx->u[2] == 0.0f && ctx->v[0] == 0.0f && ctx->v[1] == 1.0f &&
                       ctx->v[2] == 0.0f && ctx->lens_radius == 0.05;
     // several pixels per thread trade parallelism for fewer divergent rejection-loop trips:
-    // that pays once the batch fills every SM a few times over (measured: seven pixels per
-    // thread win from 16 envs of 300x300 on; below that one pixel per thread has the lower
-    // step latency)
+    // that pays once the batch fills every SM (measured on 300 x 300 frames,
+    // profiles/r02/latency_small_batches.md: one pixel per thread has the lowest step latency
+    // up to 5 envs, four per thread from 6 to ~40, eight beyond)
     int contexts = ctx->trace_contexts;
-    if (contexts < 0)
-        contexts = p.total >= (int64_t)ctx->prop.multiProcessorCount * 9216 ? rf::kMpDefaultContexts : 0;
+    if (contexts < 0) {
+        const int64_t per_sm = p.total / std::max(ctx->prop.multiProcessorCount, 1);
+        contexts = per_sm >= 24576 ? rf::kMpDefaultContexts : per_sm >= 3584 ? 4 : 0;
+    }
     if (!fast || H > rf::kMpMaxFrame || W > rf::kMpMaxFrame) contexts = 0;
     if (contexts > 0) {
         // multi-pixel kernel: blocks are per env, kCtx * kThreads pixels each (57 KB of shared

@@ -1,5 +1,5 @@
 """Step latency (host API, rf_step_host) for small vector envs, single- vs multi-context
-tracer: picks the batch size from which 4 pixels per thread pays off."""
+tracer: picks the batch size from which several pixels per thread pay off."""
 
 import json
 import os
@@ -20,7 +20,7 @@ def main():
     rng = numpy.random.Generator(numpy.random.PCG64DXSM(1234))
     for n in (1, 2, 4, 8, 13, 16, 32, 64):
         row = {"envs": n}
-        for contexts in (0, 4, 7):
+        for contexts in (0, 4, 8):
             renderer = render.FastRenderer()
             renderer.context.set_option(_lib.OPT_TRACE_CONTEXTS, contexts)
             targets = rng.uniform(5, 10, (12, n)).astype(numpy.float32)

@@ -221,17 +221,15 @@ def test_frames_beyond_the_multi_pixel_kernels_coordinate_range(torch):
 
 
 def test_pixels_per_thread_follow_the_batch_size(torch):
-    """Default option: one pixel per thread for latency-bound small batches, eight once
-    the batch fills the GPU a few times over; both leave the same frames as the oracle
-    (covered above), here only the choice is checked."""
+    """Default option: one pixel per thread for latency-bound small batches, four once the
+    batch fills every SM, eight once it fills the GPU a few times over; all leave the same
+    frames as the oracle (covered above), here only the choice is checked."""
 
-    small, large = _renderer(samples_per_pixel=1), _renderer(samples_per_pixel=1)
-    small.update_targets([7.0]), small.update_focus_planes([6.0])
-    small.render_gray_device(300)
-    assert small.context.last_trace_kernel() == 1
-    large.update_targets([7.0] * 24), large.update_focus_planes([6.0] * 24)
-    large.render_gray_device(300)
-    assert large.context.last_trace_kernel() == 8
+    for envs, kernel in ((1, 1), (5, 1), (8, 4), (13, 4), (24, 4), (48, 8)):
+        renderer = _renderer(samples_per_pixel=1)
+        renderer.update_targets([7.0] * envs), renderer.update_focus_planes([6.0] * envs)
+        renderer.render_gray_device(300)
+        assert renderer.context.last_trace_kernel() == kernel, envs
 
 
 def test_literal_kernel_handles_a_non_default_camera(torch):
