@@ -97,9 +97,22 @@ __global__ void __launch_bounds__(kThreads, 4) trace_mp_kernel(const TraceParams
     // coordinates as a half2)
 
     const int tid = threadIdx.x;
-    const int e = blockIdx.x / blocks_per_env;
-    const int chunk = blockIdx.x - e * blocks_per_env;
     const int hw = p.H * p.W;
+    // Block order: every env's full chunks first, then the envs' last, partly filled chunks.
+    // A partly filled block has fewer pixels per thread and ends sooner (at 300 x 300 its
+    // threads own one or two pixels instead of eight), so the launch ends on short blocks:
+    // the idle tail while the last blocks drain is what 8-GPU scaling loses at 512 envs per
+    // GPU (44 waves of ~1 ms blocks).
+    const int full_per_env = hw / (kCtx * kThreads);
+    int e, chunk;
+    if ((int64_t)blockIdx.x < (int64_t)p.n * full_per_env) {
+        e = blockIdx.x / full_per_env;
+        chunk = blockIdx.x - e * full_per_env;
+    } else {
+        e = (int)((int64_t)blockIdx.x - (int64_t)p.n * full_per_env);
+        chunk = full_per_env;
+    }
+    (void)blocks_per_env;
     const int first = chunk * (kCtx * kThreads);  // first pixel of this block within the env
     uint32_t sbase;  // state slot of context 0 (opaque to the compiler: it would otherwise
                      // recompute the address from the thread index at every use)

@@ -169,22 +169,24 @@ def test_multi_context_kernel_equals_literal_kernel(torch, contexts, height, n):
     numpy.testing.assert_array_equal(tested.context.rng_export(), literal.context.rng_export())
 
 
+@pytest.mark.parametrize("contexts", [4, 7, 8])
 @pytest.mark.parametrize("height,spp,n", [(1200, 2, 2), (601, 3, 1), (300, 100, 1)])
-def test_multi_context_kernel_at_sweep_sizes_matches_oracle(torch, height, spp, n):
-    """The 7-pixels-per-thread tracer at the sweep's frame sizes (and an odd one), gray path,
-    against the oracle: pixels and the RNG states left behind."""
+def test_multi_context_kernel_at_sweep_sizes_matches_oracle(torch, height, spp, n, contexts):
+    """The multi-pixel tracer (4 and 8 pixels per thread are what the library picks by batch
+    size, 7 was round 1's) at the sweep's frame sizes (and an odd one), gray path, against the
+    oracle: pixels and the RNG states left behind."""
 
     from reinfocus_b200 import _lib
 
     targets, planes = [6.25, 9.5][:n], [7.0, 9.0][:n]
     gpu = _renderer(samples_per_pixel=spp)
-    gpu.context.set_option(_lib.OPT_TRACE_CONTEXTS, 7)
+    gpu.context.set_option(_lib.OPT_TRACE_CONTEXTS, contexts)
     cpu = oracle.OracleFastRenderer(samples_per_pixel=spp, profile=oracle.PROFILE_GPU)
     for renderer in (gpu, cpu):
         renderer.update_targets(targets)
         renderer.update_focus_planes(planes)
     gray = gpu.render_gray_device(height).cpu().numpy()
-    assert gpu.context.last_trace_kernel() == 7
+    assert gpu.context.last_trace_kernel() == contexts
     numpy.testing.assert_array_equal(gray, oracle.gray(cpu.render(height)))
     numpy.testing.assert_array_equal(gpu.context.rng_export(), cpu.states)
 
@@ -198,7 +200,7 @@ def test_frames_beyond_the_multi_pixel_kernels_coordinate_range(torch):
 
     height, spp = 2052, 1
     gpu = _renderer(samples_per_pixel=spp)
-    gpu.context.set_option(_lib.OPT_TRACE_CONTEXTS, 7)
+    gpu.context.set_option(_lib.OPT_TRACE_CONTEXTS, 8)
     cpu = oracle.OracleFastRenderer(samples_per_pixel=spp, profile=oracle.PROFILE_GPU)
     for renderer in (gpu, cpu):
         renderer.update_targets([8.0])
@@ -208,13 +210,13 @@ def test_frames_beyond_the_multi_pixel_kernels_coordinate_range(torch):
     numpy.testing.assert_array_equal(gray, oracle.gray(cpu.render(height)))
     # 2048 itself is inside the range: the largest frame of the multi-pixel kernel
     edge = _renderer(samples_per_pixel=spp)
-    edge.context.set_option(_lib.OPT_TRACE_CONTEXTS, 7)
+    edge.context.set_option(_lib.OPT_TRACE_CONTEXTS, 8)
     edge_cpu = oracle.OracleFastRenderer(samples_per_pixel=spp, profile=oracle.PROFILE_GPU)
     for renderer in (edge, edge_cpu):
         renderer.update_targets([8.0])
         renderer.update_focus_planes([7.0])
     gray = edge.render_gray_device(2048).cpu().numpy()
-    assert edge.context.last_trace_kernel() == 7
+    assert edge.context.last_trace_kernel() == 8
     numpy.testing.assert_array_equal(gray, oracle.gray(edge_cpu.render(2048)))
     with pytest.raises(AssertionError):
         edge.context.set_option(_lib.OPT_TRACE_CONTEXTS, 9)
