@@ -173,9 +173,13 @@ __global__ void __launch_bounds__(kThreads, 4) trace_mp_kernel(const TraceParams
                 Rng32 st = lds_state(a);
                 uint32_t xy_bits;
                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xy_bits) : "r"(a + kWork + 12));
-                const float2 xy = __half22float2(*reinterpret_cast<const __half2 *>(&xy_bits));
-                s = pixel_coordinate((double)xy.x, rng32_next_scaled(st), Wd, Wrcp);
-                t = pixel_coordinate((double)xy.y, rng32_next_scaled(st), Hd, Hrcp);
+                // half -> double in one conversion each (F2F.F64.F16 on either half of the word)
+                double xd, yd;
+                asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f64.f16 %0, lo;\n\tcvt.f64.f16 %1, hi;\n\t}"
+                    : "=d"(xd), "=d"(yd)
+                    : "r"(xy_bits));
+                s = pixel_coordinate(xd, rng32_next_scaled(st), Wd, Wrcp);
+                t = pixel_coordinate(yd, rng32_next_scaled(st), Hd, Hrcp);
                 sts_state(a, st);
             }
             if (c & 1) { va[c >> 1].y = s; vb[c >> 1].y = t; } else { va[c >> 1].x = s; vb[c >> 1].x = t; }
