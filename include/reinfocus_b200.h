@@ -314,12 +314,15 @@ int rf_env_import(rf_env *env, const float *h_states, const float *h_old_obs, co
  *   RF_SELFTEST_INV_LENGTH  branch-free 1/sqrt-length vs __frcp_rn(__fsqrt_rn()) for every
  *                           float32 in [2^-60, 2^60];
  *   RF_SELFTEST_CONST_DIV   hoisted-reciprocal float32 division vs __fdiv_rn for every
- *                           numerator in [0, c], over `arg` divisors c spread over [0.5, 8). */
+ *                           numerator in [0, c], over `arg` divisors c spread over [0.5, 8);
+ *   RF_SELFTEST_CHECKER_PAIR  the multi-pixel tracer's FMA-pipe checker parity (RZ / RU fused
+ *                           multiply-adds) vs the table-based cell, every float32 u in [0, 1]. */
 enum {
     RF_SELFTEST_CHECKER = 0,
     RF_SELFTEST_PIXEL_DIV = 1,
     RF_SELFTEST_INV_LENGTH = 2,
-    RF_SELFTEST_CONST_DIV = 3
+    RF_SELFTEST_CONST_DIV = 3,
+    RF_SELFTEST_CHECKER_PAIR = 4
 };
 int rf_selftest(rf_ctx *ctx, int which, int arg, int64_t *mismatches, void *stream);
 /* Options. RF_OPT_FORCE_GENERIC = 1 makes rf_render use the literal any-camera kernel and

@@ -21,7 +21,7 @@ RF_ERR_NO_SCENE = -4
 
 ABI_VERSION = 9
 
-SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH, SELFTEST_CONST_DIV = 0, 1, 2, 3
+SELFTEST_CHECKER, SELFTEST_PIXEL_DIV, SELFTEST_INV_LENGTH, SELFTEST_CONST_DIV, SELFTEST_CHECKER_PAIR = 0, 1, 2, 3, 4
 OPT_FORCE_GENERIC = 0
 OPT_TRACE_CONTEXTS = 1
 INFO_LAST_TRACE_KERNEL = 0

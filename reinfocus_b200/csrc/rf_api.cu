@@ -210,7 +210,7 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
         auto launch = [&](auto kernel) -> int {
             if (smem > 48 * 1024)
                 RF_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kernel<<<(unsigned)grid, threads, smem, stream>>>(p, blocks_per_env);
+            kernel<<<(unsigned)grid, threads, smem, stream>>>(p);
             return RF_OK;
         };
         int rc = RF_OK;
@@ -1184,6 +1184,9 @@ int rf_selftest(rf_ctx *ctx, int which, int arg, int64_t *mismatches, void *stre
         case RF_SELFTEST_CONST_DIV:
             RF_REQUIRE(ctx, arg > 0 && arg <= 4096, "rf_selftest: divisor count out of range");
             rf::const_div_selftest_kernel<<<blocks, 256, 0, s>>>(arg, ctx->d_misc);
+            break;
+        case RF_SELFTEST_CHECKER_PAIR:
+            rf::checker_pair_selftest_kernel<<<blocks, 256, 0, s>>>(ctx->d_misc);
             break;
         default:
             return fail(ctx, RF_ERR_INVALID, "rf_selftest: unknown test %d", which);

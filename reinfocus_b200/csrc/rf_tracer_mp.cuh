@@ -1,11 +1,31 @@
-// Step-path tracer, second generation: trace_mp_kernel<kCtx, kThreads>.
+// Step-path tracer: trace_mp_kernel<kCtx, kThreads>, several pixels per thread.
 //
-// Same contract and the same bytes as trace_mc_kernel (rf_tracer.cuh): the default-camera
-// statement of FastRenderer._device_render (reference graphics/render.py:190-246), several
-// pixels ("contexts") per thread, the two rejection loops shared across a lane's pixels. What
-// changed is how the instructions are spent (ncu on the first generation: 315 warp
-// instructions per 32 pixel-samples, 147 of them on the ALU pipe, which at 2 cycles per warp
-// instruction is what binds the kernel; 31 were BSSY / BSYNC / BRA and 8 PLOP3):
+// Same contract and the same bytes as trace_kernel<true> (rf_tracer.cuh): the default-camera
+// statement of FastRenderer._device_render (reference graphics/render.py:190-246 and callees),
+// every pixel consuming its own xoroshiro128+ stream in the reference's order.
+//
+// What bounds the tracer on sm_100a is the ALU pipe under xoroshiro128+ (11 LOP3 / SHF / IADD3
+// per draw, one warp instruction per 2 clocks), and a warp executes about twice the draws its
+// lanes need: the two rejection loops run until the slowest of 32 lanes accepts (disc: 3.1
+// warp iterations for 1.27 per lane; sphere: 6.0 for 1.9). The streams of different pixels
+// are independent, so a lane that owns kCtx pixels ("contexts") spends the iterations it would
+// have idled through on its next pixel: the warp then iterates max-over-lanes of a SUM of kCtx
+// geometric counts, whose mean per pixel drops (disc 3.1 -> 1.8, sphere 6.0 -> 3.1 at kCtx = 8).
+//
+// Each thread owns kCtx pixels of one env (pixel = block base + c*kThreads + tid). Per sample
+// the work is split into phases that every lane runs in lock step:
+//   J  per context: two jitter draws -> (s, t) in registers           straight line
+//   D  disc rejection over the lane's contexts, one after another     shared loop
+//   H  per pair of contexts: ray + hit test + checker parity          straight line, packed
+//   S  sphere rejection over the lane's contexts that hit             shared loop
+//   C  per pair of contexts: shade, accumulate                        straight line, packed
+// The context a loop is working on changes per lane, so per-context data lives in shared
+// memory ([slot][ctx][thread], conflict-free 128-bit accesses), addressed by a per-lane
+// running pointer; only the active RNG state sits in registers.
+//
+// How the instructions are spent (round 1's kernel, same structure: 315 warp instructions per
+// 32 pixel-samples, 147 on the ALU pipe, 31 BSSY / BSYNC / BRA, 8 PLOP3; this one: 261 / 133 /
+// 11 / 0):
 //
 //   * the rejection loops carry one branch each. The accept path (store the sample and the
 //     RNG state, step to the lane's next pixel, fetch its state) is predicated inline PTX
@@ -29,7 +49,7 @@
 namespace rf {
 
 constexpr int kMpMaxFrame = 2048;  // half-precision pixel coordinates
-constexpr int kMpDefaultContexts = 8;  // 8 x 224 threads: 352.1 ms at 4096 envs; 7 x 256: 353.8
+constexpr int kMpDefaultContexts = 8;  // 8 x 224 threads: 350.7 ms per 4096-env launch; 7 x 256: 353.4
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -79,6 +99,36 @@ __device__ __forceinline__ CheckerPair checker_pair(float2 u, float2 v) {
     return r;
 }
 
+// checker_pair() against the table-based cell (checker_cell, itself checked against the
+// float64 sine by checker_selftest_kernel) for every float32 coordinate in [0, 1], each paired
+// with itself, with 0.3 and with 1: the parity where checker_pair claims exactness, and the
+// claim itself (exact iff 32 u is not an integer)
+__global__ void checker_pair_selftest_kernel(unsigned long long *mismatches) {
+    const uint32_t one_bits = 0x3f800000u;
+    unsigned long long bad = 0;
+    for (uint64_t bits = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; bits <= one_bits;
+         bits += (uint64_t)gridDim.x * blockDim.x) {
+        const float u = __uint_as_float((uint32_t)bits);
+        const float t = u * 32.0f;
+        const bool integral = __int2float_rn(__float2int_rd(t)) == t;
+        const float others[3] = {u, 0.3f, 1.0f};
+        for (int k = 0; k < 3; ++k) {
+            const float v = others[k];
+            const float tv = v * 32.0f;
+            const bool v_integral = __int2float_rn(__float2int_rd(tv)) == tv;
+            const CheckerPair ck = checker_pair(f2(u, v), f2(v, u));
+            bad += ck.exact0 != (!integral && !v_integral);
+            bad += ck.exact1 != (!integral && !v_integral);
+            if (!integral && !v_integral) {
+                const uint32_t green = (uint32_t)((checker_cell(u) ^ checker_cell(v)) & 1);
+                bad += ck.green0 != green;
+                bad += ck.green1 != green;
+            }
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // acc = RN(acc + x) unless `skip` is non-zero, in place (a select would cost a move per
 // accumulator at the end of every sample)
 __device__ __forceinline__ void add_unless(float &acc, float x, uint32_t skip) {
@@ -86,7 +136,7 @@ __device__ __forceinline__ void add_unless(float &acc, float x, uint32_t skip) {
 }
 
 template <int kCtx, int kThreads>
-__global__ void __launch_bounds__(kThreads, 4) trace_mp_kernel(const TraceParams p, int blocks_per_env) {
+__global__ void __launch_bounds__(kThreads, 4) trace_mp_kernel(const TraceParams p) {
     static_assert(kCtx >= 2 && kCtx <= 8, "2..8 pixels per thread");
     constexpr int kPairs = (kCtx + 1) / 2;
     constexpr uint32_t kStride = kThreads * 16;      // bytes between contexts of one thread
@@ -112,7 +162,6 @@ __global__ void __launch_bounds__(kThreads, 4) trace_mp_kernel(const TraceParams
         e = (int)((int64_t)blockIdx.x - (int64_t)p.n * full_per_env);
         chunk = full_per_env;
     }
-    (void)blocks_per_env;
     const int first = chunk * (kCtx * kThreads);  // first pixel of this block within the env
     uint32_t sbase;  // state slot of context 0 (opaque to the compiler: it would otherwise
                      // recompute the address from the thread index at every use)

@@ -107,6 +107,16 @@ def test_hoisted_reciprocal_division_equals_ddiv_for_every_input(ctx, size):
     assert ctx.selftest(_lib.SELFTEST_PIXEL_DIV, size) == 0
 
 
+def test_fma_pipe_checker_parity_equals_the_table_for_every_float32(ctx):
+    """The multi-pixel tracer reads the checker cell parity off RZ / RU fused multiply-adds
+    (2^23 + floor(32 u) in the mantissa): same parity as the table-based cell, and "exact"
+    claimed iff 32 u is not an integer, for every float32 u in [0, 1]."""
+
+    from reinfocus_b200 import _lib
+
+    assert ctx.selftest(_lib.SELFTEST_CHECKER_PAIR) == 0
+
+
 def test_branch_free_inverse_length_equals_intrinsics_for_every_input(ctx):
     from reinfocus_b200 import _lib
 

@@ -44,7 +44,7 @@ static cudaError_t launch(const rf::TraceParams &p, int n, int H, int W) {
     const size_t smem = (size_t)per_block * 32;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kernel<<<(unsigned)((int64_t)n * blocks_per_env), T, smem>>>(p, blocks_per_env);
+    kernel<<<(unsigned)((int64_t)n * blocks_per_env), T, smem>>>(p);
     return cudaGetLastError();
 }
 
