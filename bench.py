@@ -9,7 +9,8 @@ envs in total (strong scaling: each rank owns 4096/N envs).
 
 `value`   : device-resident loop (scene already in HBM), CUDA-event timed, max over ranks.
 `e2e`     : the public API (FastRenderer.step_focus) with host buffers: host->device copy of
-            the step's parameters and device->host read of its focus values every step.
+            the step's targets / focus planes (pinned, 8 B per env) and device->host read of
+            its focus values (8 B per env) every step.
 `roofline`: the tracer kernel (dominant) against the FP32 FFMA peak measured live.
 `cpu_baseline` / `--impl reference`: the CPU oracle (C restatement of the reference, all
             host cores) on a bounded sample of the same workload.
@@ -464,7 +465,7 @@ def run_ours(args):
         },
         "rays_per_s": args.envs * HEIGHT * HEIGHT * SPP / (device_ms * 1e-3),
         "e2e": {"value": args.envs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": args.envs * (2 + 9) * 4, "d2h_bytes_per_step": args.envs * 8,
+                "h2d_bytes_per_step": args.envs * 2 * 4, "d2h_bytes_per_step": args.envs * 8,
                 "bytes_note": "whole job; each rank copies 1/n_gpus of it"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),

@@ -184,6 +184,13 @@ typedef struct {
 } rf_scene_packing;
 int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float *d_planes,
                         int stride, const rf_scene_packing *packing, void *stream);
+/* rf_step_host for callers that hold the positions themselves, not packed parameters: host
+ * targets / focus planes in (float32 [n] each), host float64 focus values out; the packing of
+ * FastWorlds / FastCameras._make_device_data runs on the GPU (rf_set_scene_device). One call
+ * = one FocusObserver.observe (reference environments/state_observer.py:377-383).
+ * Synchronous. */
+int rf_step_positions_host(rf_ctx *ctx, int n, int H, int spp, const float *h_targets, const float *h_planes,
+                           const rf_scene_packing *packing, double *h_focus, void *stream);
 
 /* -------------------------------------------------------------------------------------
  * Device-resident vector env. Replaces reference environments/vector_environment.py:75-164

@@ -133,6 +133,8 @@ _SIGNATURES = {
                                 ctypes.c_int, _vp, _vp]),
     "rf_focus_planes": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
                                        ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "rf_step_positions_host": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp,
+                                              ctypes.POINTER(ScenePacking), _vp, _vp]),
     "rf_step_host": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp,
                                     _vp, _vp]),
     "rf_step_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
@@ -359,6 +361,12 @@ class Context:
                   h_cam_dyn: int | None, h_focus: int, stream=None):
         self._check(self._lib.rf_step_host(self._handle, n, height, spp, _vp(h_world),
                                            _vp(h_cam_dyn), _vp(h_focus), _stream_ptr(stream, self.device)))
+
+    def step_positions_host(self, n: int, height: int, spp: int, h_targets: int, h_planes: int,
+                            packing: ScenePacking, h_focus: int, stream=None):
+        self._check(self._lib.rf_step_positions_host(self._handle, n, height, spp, _vp(h_targets), _vp(h_planes),
+                                                     ctypes.byref(packing), _vp(h_focus),
+                                                     _stream_ptr(stream, self.device)))
 
     def step_device(self, n: int, height: int, spp: int, d_focus: int, stream=None):
         self._check(self._lib.rf_step_device(self._handle, n, height, spp, _vp(d_focus),

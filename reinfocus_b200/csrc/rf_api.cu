@@ -58,6 +58,8 @@ struct rf_ctx {
     double *d_focus = nullptr;
     int cap_focus_out = 0;
     unsigned long long *d_misc = nullptr;  // small scratch (selftests)
+    float *d_positions = nullptr;          // [2, cap_positions] targets, focus planes (rf_step_positions_host)
+    int cap_positions = 0;
 
     // general-scene path (rf_render_generic): scene scratch, pristine seed states + working copy
     uint8_t *d_generic_scene = nullptr;
@@ -424,6 +426,7 @@ int rf_destroy(rf_ctx *ctx) {
     cudaFree(ctx->d_gray);
     cudaFree(ctx->d_focus);
     cudaFree(ctx->d_misc);
+    cudaFree(ctx->d_positions);
     cudaFree(ctx->d_generic_scene);
     cudaFree(ctx->d_generic_pristine);
     cudaFree(ctx->d_generic_states);
@@ -766,6 +769,31 @@ int rf_set_scene_device(rf_ctx *ctx, int n, const float *d_targets, const float 
     RF_CUDA(ctx, cudaGetLastError());
     ctx->n_world = ctx->n_cam = n;
     ctx->have_world = ctx->have_cam = true;
+    return RF_OK;
+}
+
+int rf_step_positions_host(rf_ctx *ctx, int n, int H, int spp, const float *h_targets, const float *h_planes,
+                           const rf_scene_packing *packing, double *h_focus, void *stream) {
+    RF_REQUIRE(ctx, ctx != nullptr, "rf_step_positions_host: ctx is NULL");
+    RF_REQUIRE(ctx, n > 0 && h_targets && h_planes && packing && h_focus, "rf_step_positions_host: empty batch");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n > ctx->cap_positions) {
+        RF_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->cap_positions = 0;
+        const int cap = std::max(n, 64);
+        if (int rc = grow(ctx, (void **)&ctx->d_positions, sizeof(float) * 2 * (size_t)cap)) return rc;
+        ctx->cap_positions = cap;
+    }
+    float *d_targets = ctx->d_positions, *d_planes = ctx->d_positions + ctx->cap_positions;
+    RF_CUDA(ctx, cudaMemcpyAsync(d_targets, h_targets, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s));
+    RF_CUDA(ctx, cudaMemcpyAsync(d_planes, h_planes, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s));
+    if (int rc = rf_set_scene_device(ctx, n, d_targets, d_planes, 1, packing, stream)) return rc;
+    if (int rc = check_render_args(ctx, "rf_step_positions_host", n, H, H, spp)) return rc;
+    if (int rc = ensure_step_scratch(ctx, n, H, s)) return rc;
+    if (int rc = rf_step_device(ctx, n, H, spp, ctx->d_focus, stream)) return rc;
+    RF_CUDA(ctx, cudaMemcpyAsync(h_focus, ctx->d_focus, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    RF_CUDA(ctx, cudaStreamSynchronize(s));
     return RF_OK;
 }
 

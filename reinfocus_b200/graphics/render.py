@@ -75,17 +75,31 @@ class FastRenderer:
         self._uploaded_world = -1
         self._uploaded_cameras = -1
         self._pinned = {}
+        self._packing = None   # rf_scene_packing of this renderer's worlds / cameras
+        self._pending = None   # (targets, focus planes) of a step_focus not yet in the DeviceData
 
     # ------------------------------------------------------------ reference methods
     def update_targets(self, targets: Collection[float]):
         """reference render.py:147-154"""
 
+        self._flush_pending()
         self._worlds.update(targets)
 
     def update_focus_planes(self, focus_planes: Collection[float]):
         """reference render.py:156-163"""
 
+        self._flush_pending()
         self._cameras.update(focus_planes)
+
+    def _flush_pending(self):
+        """``step_focus`` hands the positions straight to the library; the host-side
+        ``DeviceData`` (what ``render`` / ``len`` / a later partial update see) catches up here."""
+
+        if self._pending is not None:
+            targets, focus_planes = self._pending
+            self._pending = None
+            self._worlds.update(targets)
+            self._cameras.update(focus_planes)
 
     def render(self, frame_height: int) -> NDArray[numpy.uint8]:
         """reference render.py:165-188: uint8 RGB frames (n, H, H, 3) on the host."""
@@ -102,9 +116,11 @@ class FastRenderer:
         return self._samples_per_pixel
 
     def __len__(self) -> int:
+        self._flush_pending()
         return len(self._worlds)
 
     def _sync_scene(self) -> int:
+        self._flush_pending()
         world_data = self._worlds.device_data()  # AssertionError before the first update
         cam_data = self._cameras.device_data()
         n = len(self._worlds)
@@ -158,7 +174,9 @@ class FastRenderer:
         """The constants of the host packing (FastWorlds / FastCameras ._make_device_data)
         for rf_set_scene_device, which does that packing on the GPU."""
 
-        return _lib.ScenePacking(self._worlds.packing_constant, *self._cameras.packing_constants)
+        if self._packing is None:
+            self._packing = _lib.ScenePacking(self._worlds.packing_constant, *self._cameras.packing_constants)
+        return self._packing
 
     def scene_overwritten(self):
         """Tells the renderer that someone (rf_set_scene_device, a device env) replaced the
@@ -189,39 +207,39 @@ class FastRenderer:
     def step_focus(self, targets: Collection[float], focus_planes: Collection[float],
                    frame_height: int = 300) -> NDArray[numpy.float64]:
         """One FocusObserver.observe (reference state_observer.py:377-383) in a single
-        C-ABI call: host targets / focus planes in, host float64 focus values out."""
+        C-ABI call: host targets / focus planes in, host float64 focus values out. Equivalent
+        to update_targets + update_focus_planes + vision.focus_values(render(frame_height)):
+        the positions go to the GPU as they are (8 bytes per env) and the packing of
+        FastWorlds / FastCameras runs there (rf_step_positions_host), bit for bit what the host
+        classes compute."""
 
         import torch
 
-        self.update_targets(targets)
-        self.update_focus_planes(focus_planes)
-        world_data = self._worlds.device_data()
-        cam_data = self._cameras.device_data()
-        n = len(self._worlds)
-        assert len(self._cameras) >= n
-        upload_world = self._uploaded_world != self._worlds.version
-        upload_cameras = self._uploaded_cameras != self._cameras.version
-        if self._uploaded_cameras < 0:
-            # first use: the statics (origin, u, v, lens) travel by value with
-            # rf_set_cameras; afterwards only the dynamic part is copied, inside rf_step_host
-            self._ctx.set_cameras(cam_data, *self._cameras.statics)
+        targets = numpy.asarray(targets, dtype=numpy.float32)
+        focus_planes = numpy.asarray(focus_planes, dtype=numpy.float32)
+        assert targets.ndim == 1 and focus_planes.ndim == 1, "expected one value per environment"
+        n = len(targets)
+        assert len(focus_planes) >= n, f"{n} targets but only {len(focus_planes)} focus planes were set"
+        if n == 0:
+            self.update_targets(targets)
+            self.update_focus_planes(focus_planes)
+            return numpy.empty((0,), dtype=numpy.float64)
         # pinned staging buffers, grown on demand and reused for smaller batches (the vector
         # env alternates between all n envs and the k that restarted)
         if self._pinned.get("capacity", 0) < n:
             capacity = max(n, 2 * self._pinned.get("capacity", 0))
             self._pinned = {"capacity": capacity,
-                            "world": torch.empty((capacity, 2), dtype=torch.float32).pin_memory(),
-                            "cameras": torch.empty((capacity, 9), dtype=torch.float32).pin_memory(),
+                            "targets": torch.empty((capacity,), dtype=torch.float32).pin_memory(),
+                            "planes": torch.empty((capacity,), dtype=torch.float32).pin_memory(),
                             "focus": torch.empty((capacity,), dtype=torch.float64).pin_memory()}
-        h_world, h_cam, h_focus = (self._pinned[name][:n] for name in ("world", "cameras", "focus"))
-        if upload_world:
-            h_world.numpy()[...] = world_data
-        if upload_cameras:
-            h_cam.numpy()[...] = cam_data[:n].reshape(n, 9)
-        self._ctx.step_host(n, frame_height, self._samples_per_pixel,
-                            h_world.data_ptr() if upload_world else None,
-                            h_cam.data_ptr() if upload_cameras else None,
-                            h_focus.data_ptr())
-        self._uploaded_world = self._worlds.version
-        self._uploaded_cameras = self._cameras.version
-        return h_focus.numpy().copy()
+            self._pinned["views"] = tuple(self._pinned[name].numpy() for name in ("targets", "planes", "focus"))
+            self._pinned["pointers"] = tuple(self._pinned[name].data_ptr() for name in ("targets", "planes", "focus"))
+        h_targets, h_planes, h_focus = self._pinned["views"]
+        h_targets[:n] = targets
+        h_planes[:n] = focus_planes[:n]
+        self._ctx.step_positions_host(n, frame_height, self._samples_per_pixel, *self._pinned["pointers"][:2],
+                                      self.scene_packing(), self._pinned["pointers"][2])
+        # the context now holds this scene; the DeviceData objects learn about it lazily
+        self._pending = (targets.copy(), focus_planes.copy())
+        self.scene_overwritten()
+        return h_focus[:n].copy()

@@ -1,5 +1,5 @@
-"""Where a small-batch step goes: FastRenderer.step_focus (Python packing + C call) vs the C
-call alone (rf_step_host on pinned buffers) vs the two kernels (CUDA events)."""
+"""Where a small-batch step goes: FastRenderer.step_focus (Python staging + C call) vs the C
+call alone (rf_step_positions_host on pinned buffers) vs the two kernels (CUDA events)."""
 
 import json
 import os
@@ -29,11 +29,11 @@ def main():
         for i in range(8, 40):
             renderer.step_focus(targets[i], planes[i], 300)
         full = (time.perf_counter() - t0) / 32 * 1e3
-        pinned = renderer._pinned
-        h_world, h_cam, h_focus = (pinned[name][:n] for name in ("world", "cameras", "focus"))
+        h_targets, h_planes, h_focus = renderer._pinned["pointers"]
+        packing = renderer.scene_packing()
         t0 = time.perf_counter()
         for i in range(32):
-            ctx.step_host(n, 300, 100, h_world.data_ptr(), h_cam.data_ptr(), h_focus.data_ptr())
+            ctx.step_positions_host(n, 300, 100, h_targets, h_planes, packing, h_focus)
         c_call = (time.perf_counter() - t0) / 32 * 1e3
         gray = torch.empty((n, 300, 300), dtype=torch.uint8, device="cuda")
         focus = torch.empty((n,), dtype=torch.float64, device="cuda")
