@@ -233,15 +233,36 @@ def test_frames_beyond_the_multi_pixel_kernels_coordinate_range(torch):
 
 
 def test_pixels_per_thread_follow_the_batch_size(torch):
-    """Default option: one pixel per thread for latency-bound small batches, four once the
-    batch fills every SM, eight once it fills the GPU a few times over; all leave the same
-    frames as the oracle (covered above), here only the choice is checked."""
+    """Default option: one pixel per thread for one or two envs, four from three on (in small
+    blocks that spread over the SMs), eight once the batch fills the GPU; all leave the same
+    frames as the oracle (below), here only the choice is checked."""
 
-    for envs, kernel in ((1, 1), (5, 1), (8, 4), (13, 4), (24, 4), (48, 8)):
+    for envs, kernel in ((1, 1), (2, 1), (3, 4), (5, 4), (8, 4), (13, 4), (24, 8), (48, 8), (64, 8)):
         renderer = _renderer(samples_per_pixel=1)
         renderer.update_targets([7.0] * envs), renderer.update_focus_planes([6.0] * envs)
         renderer.render_gray_device(300)
         assert renderer.context.last_trace_kernel() == kernel, envs
+
+
+@pytest.mark.parametrize("envs", [3, 8, 24, 64])
+def test_default_kernel_choice_matches_oracle_at_every_batch_size_class(torch, envs):
+    """The kernels the library picks by itself for small and medium batches (4 x 64, 4 x 128,
+    8 x 128 and 8 x 224 pixels x threads) against the oracle: gray frames and RNG states."""
+
+    height, spp = 300, 2
+    rng = numpy.random.default_rng(envs)
+    targets = rng.uniform(5, 10, envs).astype(numpy.float32)
+    planes = rng.uniform(5, 10, envs).astype(numpy.float32)
+    gpu = _renderer(samples_per_pixel=spp)
+    cpu = oracle.OracleFastRenderer(samples_per_pixel=spp, profile=oracle.PROFILE_GPU)
+    for renderer in (gpu, cpu):
+        renderer.update_targets(targets)
+        renderer.update_focus_planes(planes)
+    for _ in range(2):  # twice: the states of the first call feed the second
+        gray = gpu.render_gray_device(height).cpu().numpy()
+        assert gpu.context.last_trace_kernel() in (4, 8)
+        numpy.testing.assert_array_equal(gray, oracle.gray(cpu.render(height)))
+    numpy.testing.assert_array_equal(gpu.context.rng_export(), cpu.states)
 
 
 def test_literal_kernel_handles_a_non_default_camera(torch):

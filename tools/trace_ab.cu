@@ -119,6 +119,8 @@ int main(int argc, char **argv) {
 
     auto run = [&]() -> cudaError_t {
         switch (ctx) {
+            case 2: return launch<2>(p, n, H, W);
+            case 3: return launch<3>(p, n, H, W);
             case 4: return launch<4>(p, n, H, W);
             case 6: return launch<6>(p, n, H, W);
             case 7: return launch<7>(p, n, H, W);
