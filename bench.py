@@ -514,9 +514,9 @@ def run_ours(args):
             "resets_per_step_rank0": device_resets / args.steps,
         },
         "step_breakdown": dict(breakdown, timed_loop_ms_per_step=device_ms,
-                               blocks_per_gpu=n_local * ((HEIGHT * HEIGHT + 1791) // 1792),
-                               resident_blocks_per_gpu=info["sm_count"] * 4,
-                               note="the tracer runs 4 blocks of 1792 pixels x 100 samples per SM; a block lasts "
+                               blocks_per_gpu=n_local * ((HEIGHT * HEIGHT + 2047) // 2048),
+                               resident_blocks_per_gpu=info["sm_count"] * 3,
+                               note="the tracer runs 3 blocks of 2048 pixels x 100 samples per SM; a block lasts "
                                     "trace_ms / waves, and the launch ends with up to one block time of partly "
                                     "idle SMs - a fixed cost that weighs more the fewer envs a GPU owns"),
         "rng_init_s": rng_init_s,

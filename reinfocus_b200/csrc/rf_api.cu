@@ -194,22 +194,21 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
     // and small blocks spread a small grid evenly over the SMs. Measured on 300 x 300 frames
     // (tools/trace_ab.cu over envs x pixels per thread x block size,
     // profiles/r02/latency_small_batches.md): one pixel per thread up to 2 envs, 4 x 64 threads
-    // from 3 to 7, 4 x 128 to 19, 8 x 128 to ~55, 8 x 224 beyond. An explicit
-    // RF_OPT_TRACE_CONTEXTS keeps the large blocks.
+    // from 3 to 7, 4 x 128 to ~24, 8 x 256 beyond. An explicit RF_OPT_TRACE_CONTEXTS keeps
+    // 256-thread blocks.
     int contexts = ctx->trace_contexts;
-    int threads = contexts == 8 ? 224 : 256;
+    int threads = contexts == 8 ? rf::kMpDefaultThreads : 256;
     if (contexts < 0) {
         const int64_t per_sm = p.total / std::max(ctx->prop.multiProcessorCount, 1);
-        if (per_sm >= 34000) contexts = rf::kMpDefaultContexts, threads = 224;
-        else if (per_sm >= 12000) contexts = 8, threads = 128;
+        if (per_sm >= 15000) contexts = rf::kMpDefaultContexts, threads = rf::kMpDefaultThreads;
         else if (per_sm >= 4300) contexts = 4, threads = 128;
         else if (per_sm >= 1500) contexts = 4, threads = 64;
         else contexts = 0;
     }
     if (!fast || H > rf::kMpMaxFrame || W > rf::kMpMaxFrame) contexts = 0;
     if (contexts > 0) {
-        // multi-pixel kernel: blocks are per env, kCtx * kThreads pixels each (57 KB of shared
-        // memory at 7 x 256 and at 8 x 224: four blocks per SM either way)
+        // multi-pixel kernel: blocks are per env, kCtx * kThreads pixels each, 32 B of shared
+        // memory per pixel (64 KB at 8 x 256: three blocks per SM at 80 registers)
         const int per_block = contexts * threads;
         const int blocks_per_env = (H * W + per_block - 1) / per_block;
         const int64_t grid = (int64_t)n * blocks_per_env;
@@ -229,10 +228,9 @@ int launch_trace(rf_ctx *ctx, int n, int H, int W, int spp, uint8_t *d_rgb, uint
             case 5256: rc = launch(rf::trace_mp_kernel<5, 256>); break;
             case 6256: rc = launch(rf::trace_mp_kernel<6, 256>); break;
             case 7256: rc = launch(rf::trace_mp_kernel<7, 256>); break;
-            case 8224: rc = launch(rf::trace_mp_kernel<8, 224>); break;
+            case 8256: rc = launch(rf::trace_mp_kernel<8, 256, rf::kMpDefaultBlocks>); break;
             case 4064: rc = launch(rf::trace_mp_kernel<4, 64>); break;
             case 4128: rc = launch(rf::trace_mp_kernel<4, 128>); break;
-            case 8128: rc = launch(rf::trace_mp_kernel<8, 128>); break;
             default:
                 return fail(ctx, RF_ERR_INVALID, "unsupported context count %d", contexts);
         }

@@ -49,7 +49,13 @@
 namespace rf {
 
 constexpr int kMpMaxFrame = 2048;  // half-precision pixel coordinates
-constexpr int kMpDefaultContexts = 8;  // 8 x 224 threads: 350.7 ms per 4096-env launch; 7 x 256: 353.4
+// pixels per thread, threads per block and blocks per SM of large batches: 8 x 256 x 3 (64 KB of
+// shared memory per block, 80 registers, 24 warps per SM; 2048 pixels per block leave the last
+// of a 300 x 300 env's 44 blocks 95 % full): 341.9 ms per 4096-env launch; 8 x 192 x 4: 346.0;
+// 8 x 224 x 4 (72 registers): 350.4; 7 x 256 x 4 (64 registers): 353.4
+constexpr int kMpDefaultContexts = 8;
+constexpr int kMpDefaultThreads = 256;
+constexpr int kMpDefaultBlocks = 3;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -135,8 +141,10 @@ __device__ __forceinline__ void add_unless(float &acc, float x, uint32_t skip) {
     asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p add.rn.f32 %0, %0, %1;\n\t}" : "+f"(acc) : "f"(x), "r"(skip));
 }
 
-template <int kCtx, int kThreads>
-__global__ void __launch_bounds__(kThreads, 4) trace_mp_kernel(const TraceParams p) {
+// kMinBlocks: resident blocks per SM the register allocation must allow (4: at most 64
+// registers at 256 threads; 3: 85)
+template <int kCtx, int kThreads, int kMinBlocks = 4>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) trace_mp_kernel(const TraceParams p) {
     static_assert(kCtx >= 2 && kCtx <= 8, "2..8 pixels per thread");
     constexpr int kPairs = (kCtx + 1) / 2;
     constexpr uint32_t kStride = kThreads * 16;      // bytes between contexts of one thread

@@ -237,7 +237,7 @@ def test_pixels_per_thread_follow_the_batch_size(torch):
     blocks that spread over the SMs), eight once the batch fills the GPU; all leave the same
     frames as the oracle (below), here only the choice is checked."""
 
-    for envs, kernel in ((1, 1), (2, 1), (3, 4), (5, 4), (8, 4), (13, 4), (24, 8), (48, 8), (64, 8)):
+    for envs, kernel in ((1, 1), (2, 1), (3, 4), (5, 4), (8, 4), (13, 4), (24, 4), (32, 8), (64, 8)):
         renderer = _renderer(samples_per_pixel=1)
         renderer.update_targets([7.0] * envs), renderer.update_focus_planes([6.0] * envs)
         renderer.render_gray_device(300)
@@ -246,8 +246,8 @@ def test_pixels_per_thread_follow_the_batch_size(torch):
 
 @pytest.mark.parametrize("envs", [3, 8, 24, 64])
 def test_default_kernel_choice_matches_oracle_at_every_batch_size_class(torch, envs):
-    """The kernels the library picks by itself for small and medium batches (4 x 64, 4 x 128,
-    8 x 128 and 8 x 224 pixels x threads) against the oracle: gray frames and RNG states."""
+    """The kernels the library picks by itself for small and medium batches (4 x 64, 4 x 128
+    and 8 x 256 pixels x threads) against the oracle: gray frames and RNG states."""
 
     height, spp = 300, 2
     rng = numpy.random.default_rng(envs)

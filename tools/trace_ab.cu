@@ -17,6 +17,9 @@
 #ifndef RF_AB_THREADS
 #define RF_AB_THREADS 256
 #endif
+#ifndef RF_AB_MIN_BLOCKS
+#define RF_AB_MIN_BLOCKS 4
+#endif
 
 #define CK(call)                                                                          \
     do {                                                                                  \
@@ -38,7 +41,7 @@ __global__ void checksum_kernel(const uint32_t *words, int64_t n, unsigned long 
 template <int K>
 static cudaError_t launch(const rf::TraceParams &p, int n, int H, int W) {
     constexpr int T = RF_AB_THREADS;
-    auto kernel = rf::trace_mp_kernel<K, T>;
+    auto kernel = rf::trace_mp_kernel<K, T, RF_AB_MIN_BLOCKS>;
     const int per_block = K * T;
     const int blocks_per_env = (H * W + per_block - 1) / per_block;
     const size_t smem = (size_t)per_block * 32;
