@@ -498,6 +498,13 @@ def run_ours(args):
             "traffic": scaled_traffic("focus_kernel_bytes_per_env"),
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
             "launch_ms": focus_ms, "algorithmic_bytes_per_launch": focus_bytes,
+            # what binds it: VIMNMX3.U16x2 / PRMT / IADD3 of the packed median and Laplacian on
+            # the ALU pipe, not memory
+            "alu": alu_view(traffic, n_local, focus_ms, info["sm_count"], clocks.summary(),
+                            key="focus_kernel_alu_warp_inst_per_env",
+                            source="static ncu capture at 4096 envs: pipe_alu active share x active cycles "
+                                   "(profiles/r02/focus_4096envs_ncu_summary.txt); peak = SMs x 4 schedulers x "
+                                   "sampled SM clock / 2"),
         },
         "env_loop": {
             "what": "VectorDiscreteSteps.step with uniform random actions: transform + render + "
@@ -558,8 +565,9 @@ def issue_view(traffic, n_local, trace_ms, sm_count, clock_summary):
             "ncu_pct": traffic.get("trace_kernel_ncu_pct")}
 
 
-def alu_view(traffic, n_local, trace_ms, sm_count, clock_summary):
-    per_env = traffic.get("trace_kernel_alu_warp_inst_per_env")
+def alu_view(traffic, n_local, trace_ms, sm_count, clock_summary, key="trace_kernel_alu_warp_inst_per_env",
+             source=None):
+    per_env = traffic.get(key)
     mhz = clock_summary.get("sm_mhz") or clock_summary.get("sm_max_mhz")
     if not per_env or not mhz:
         return None
@@ -567,7 +575,8 @@ def alu_view(traffic, n_local, trace_ms, sm_count, clock_summary):
     peak = sm_count * 4 * mhz * 1e6 / 2 / 1e9
     return {"warp_inst_per_launch": per_env * n_local, "achieved": achieved, "peak": peak,
             "unit": "G ALU-pipe warp-inst/s", "frac": achieved / peak,
-            "source": "static ncu capture: executed LOP3 / SHF / IADD3 / ISETP / FSETP ... per env at 256 envs "
+            "source": source or
+                      "static ncu capture: executed LOP3 / SHF / IADD3 / ISETP / FSETP ... per env at 256 envs "
                       "(profiles/r02/mp8_opcode_mix.txt); peak = SMs x 4 schedulers x sampled SM clock / 2 "
                       "(measured: tools/pipe_microbench.cu, 2.0 clocks per warp instruction)"}
 

@@ -261,13 +261,19 @@ int launch_focus_packed(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, 
     // (1 + 4 / band) * (w >= 1 ? ceil(w) / w : 1 / w) with w = tiles / resident warps.
     // A tile's sums of the Laplacian and of its square stay in 32 bits until the atomics:
     // 120 columns x 255^2 x rows < 2^32 needs rows <= 550, hence the cap.
-    const double resident = (double)ctx->prop.multiProcessorCount * 32;
+    // A last segment of at most 60 columns (W = 300: 120 + 120 + 60) is run for two envs per
+    // warp, one per half-warp, so its tiles cost half a warp each.
+    const bool shared = W - (p.segs - 1) * rf::kPackedCols <= rf::kPackedHalfCols;
+    p.full_segs = shared ? p.segs - 1 : p.segs;
+    p.pairs = shared ? (n + 1) / 2 : 0;
+    const int64_t warps_per_band = shared ? (int64_t)p.pairs * (2 * p.full_segs + 1) : (int64_t)n * p.segs;
+    const double resident = (double)ctx->prop.multiProcessorCount * rf::kPackedWarps * rf::kPackedBlocksPerSM;
     int band = std::min(H, rf::kPackedMaxBand);
     double best = 1e300;
     for (int k = 1; k <= std::max(1, H / 4); ++k) {
         const int rows = (H + k - 1) / k;
         if (rows > rf::kPackedMaxBand) continue;
-        const double w = (double)n * p.segs * ((H + rows - 1) / rows) / resident;
+        const double w = (double)warps_per_band * ((H + rows - 1) / rows) / resident;
         const double fill = w >= 1.0 ? std::ceil(w) / w : 1.0 / w;
         const double cost = (1.0 + 4.0 / rows) * fill;
         if (cost < best - 1e-12) {
@@ -277,9 +283,11 @@ int launch_focus_packed(rf_ctx *ctx, int n, int H, int W, const uint8_t *d_img, 
     }
     p.band = band;
     p.bands = (H + band - 1) / band;
+    p.one = 1u;
+    p.minus_one = ~0u;
     // warps take tiles in one flat order over all envs, so blocks stay full whatever the
     // number of tiles per env is
-    const int64_t tiles = (int64_t)n * p.segs * p.bands;
+    const int64_t tiles = warps_per_band * p.bands;
     const int64_t blocks = (tiles + rf::kPackedWarps - 1) / rf::kPackedWarps;
     if (blocks > 0x7fffffffLL) return fail(ctx, RF_ERR_INVALID, "focus batch too large");
     p.img = d_img;

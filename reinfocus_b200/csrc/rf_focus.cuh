@@ -207,10 +207,22 @@ __global__ void __launch_bounds__(kFocusThreads) focus_kernel(const FocusParams 
 // previous rows kept in registers. Borders: replicated gray (median), reflect-101 medians
 // (Laplacian), exactly as the staged kernel above. Requires W % 4 == 0, W >= 8, H >= 2 and a
 // 4-byte aligned image; anything else (and the debug planes) uses focus_kernel.
+//
+// Round 2 (the kernel is bound by the ALU pipe, which takes VIMNMX3 / PRMT / IADD3 / SEL at one
+// warp instruction per two clocks and scheduler, profiles/r02/pipe_microbench.txt):
+//   * when the last column segment is at most 60 pixels wide (W = 300: 120 + 120 + 60) a warp
+//     runs it for two envs at once, one per half-warp, instead of leaving half its lanes idle;
+//   * the rows that need a border rule (the first Laplacian row of the image's top band, the
+//     last three rows of a band) are peeled off, so the row loop has no selects or row clamps;
+//   * the median's "sum minus min minus max" runs partly as IMAD x * 1 + y on the FMA pipe,
+//     which issues beside the ALU pipe (the 1 comes from the parameter block so that ptxas
+//     keeps the multiply).
 // =========================================================================================
 
 constexpr int kPackedWarps = 8;
+constexpr int kPackedBlocksPerSM = 4;  // 54 registers; capping them at 48 for a fifth block spills in the row loop: no gain
 constexpr int kPackedCols = 120;  // productive columns per warp tile
+constexpr int kPackedHalfCols = 60;  // a last segment this narrow is run for two envs per warp
 constexpr int kPackedMaxBand = 512;  // rows per warp tile: keeps the 32-bit tile sums from wrapping
 
 struct PackedFocusParams {
@@ -221,14 +233,13 @@ struct PackedFocusParams {
     int n, H, W, channels;
     int band;         // output rows per tile
     int segs, bands;  // tiles per env = segs * bands
+    int full_segs;    // segments that own a whole warp: segs, or segs - 1 when the last one is shared
+    int pairs;        // env pairs sharing last-segment tiles: (n + 1) / 2, or 0 without sharing
+    uint32_t one, minus_one;  // 1 and -1, opaque to the compiler (IMAD adds, see above)
 };
 
 __device__ __forceinline__ uint32_t min3x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 __device__ __forceinline__ uint32_t max3x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
-// per-lane median of three: sum - min - max (16-bit lanes never overflow: 3 * 255)
-__device__ __forceinline__ uint32_t med3x2(uint32_t a, uint32_t b, uint32_t c) {
-    return a + b + c - min3x2(a, b, c) - max3x2(a, b, c);
-}
 
 template <int kChannels>
 __device__ __forceinline__ uint32_t load_gray_word(const uint8_t *row, int x, int W) {
@@ -261,20 +272,62 @@ template <int kChannels>
 __global__ void __launch_bounds__(kPackedWarps * 32) focus_packed_kernel(const PackedFocusParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t flat = (int64_t)blockIdx.x * kPackedWarps + (threadIdx.x >> 5);
-    const int tiles_per_env = p.segs * p.bands;
-    const int e = (int)(flat / tiles_per_env);
-    if (e >= p.n) return;  // whole warp
-    const int tile = (int)(flat - (int64_t)e * tiles_per_env);
-    const int seg = tile % p.segs, band = tile / p.segs;
     const int H = p.H, W = p.W;
+    // which tile: a whole warp on one env, or (last, narrow segment) a half-warp per env. The
+    // flat order keeps the warps that touch the same image rows next to each other - all
+    // segments of an (env, band), and with sharing both envs' segments and then their shared
+    // tile - so that the 32-byte sectors straddling two segments are fetched from HBM once.
+    bool shared_tile = false;  // warp-uniform
+    int e, seg, band, hl = lane;
+    bool valid = true;
+    if (p.pairs == 0) {
+        const int tiles_per_env = p.segs * p.bands;
+        e = (int)(flat / tiles_per_env);
+        if (e >= p.n) return;  // whole warp
+        const int tile = (int)(flat - (int64_t)e * tiles_per_env);
+        seg = tile % p.segs;
+        band = tile / p.segs;
+    } else {
+        const int unit = 2 * p.full_segs + 1;  // warps per (env pair, band)
+        const int64_t group = flat / unit;
+        const int k = (int)(flat - group * unit);
+        const int64_t pair = group / p.bands;
+        if (pair >= p.pairs) return;  // whole warp
+        band = (int)(group - pair * p.bands);
+        if (k < 2 * p.full_segs) {
+            const int second = k >= p.full_segs ? 1 : 0;
+            e = (int)(2 * pair) + second;
+            if (e >= p.n) return;  // odd batch: the last pair has one env
+            seg = k - second * p.full_segs;
+        } else {
+            shared_tile = true;
+            seg = p.segs - 1;
+            hl = lane & 15;
+            e = (int)(2 * pair) + (lane >> 4);
+            // an odd batch leaves the last upper half-warp without an env: it shadows the lower
+            // half's (in-bounds loads, same shuffles) and neither counts nor reports
+            valid = e < p.n;
+            if (!valid) e -= 1;
+        }
+    }
     const int y0 = band * p.band, y1 = min(y0 + p.band, H);
-    const int x0 = seg * kPackedCols - 4 + 4 * lane;
+    const int x0 = seg * kPackedCols - 4 + 4 * hl;
     // this lane's four Laplacians count iff it is a productive lane inside the image
-    const bool counts = lane >= 1 && lane <= 30 && x0 < W;
+    const bool counts = valid && hl >= 1 && (shared_tile || lane <= 30) && x0 < W;
     const bool at_left = x0 == 0, at_right = x0 + 4 == W;
 
     const uint8_t *img = p.img + (size_t)e * H * W * kChannels;
     const size_t pitch = (size_t)W * kChannels;
+    const uint32_t one = p.one, minus_one = p.minus_one;
+    // a + b + c - lo - hi with the first add and the last subtraction on the FMA pipe
+    auto middle = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t lo, uint32_t hi) -> uint32_t {
+        const uint32_t t = a * one + b;
+        const uint32_t u = t + c - lo;
+        return hi * minus_one + u;
+    };
+    auto med3x2 = [&](uint32_t a, uint32_t b, uint32_t c) -> uint32_t {
+        return middle(a, b, c, min3x2(a, b, c), max3x2(a, b, c));
+    };
 
     uint32_t a1 = 0, a2 = 0, a3 = 0, a4 = 0;  // packs of row r-2
     uint32_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;  // packs of row r-1
@@ -283,11 +336,13 @@ __global__ void __launch_bounds__(kPackedWarps * 32) focus_packed_kernel(const P
     // the Laplacian is kept non-negative per 16-bit lane by a bias of 1024, whose low byte is
     // zero: after clamping to [1024, 1279] the low bytes are the saturated Laplacians
     const uint32_t bias = 1024u | (1024u << 16), top = 1279u | (1279u << 16);
-    const uint32_t count_mask = counts ? 0xffffffffu : 0u;
     // (m-1, m0) and (m3, m4) for the Laplacian's left / right neighbours; at the image edges
     // reflect-101 makes m-1 := m1 and m4 := m2, which is just another byte selection
     const uint32_t select_left = at_left ? 0x5476u : 0x5432u;
     const uint32_t select_right = at_right ? 0x1032u : 0x5432u;
+    // the gray pair (x0+3, x0+4) takes x0+4 from the right lane's first pair, or repeats x0+3
+    // at the image's right edge (so that lane may belong to another env's half-warp)
+    const uint32_t select_c4 = at_right ? 0x1717u : 0x1017u;
 
     // gray input: one aligned word per lane and row. Lanes left / right of the image load the
     // first / last word of the row and replicate its outer byte (the border rule) with a
@@ -300,33 +355,35 @@ __global__ void __launch_bounds__(kPackedWarps * 32) focus_packed_kernel(const P
         if (kChannels == 1) return __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(row_ptr)), 0u, replicate);
         return load_gray_word<kChannels>(img + (size_t)min(max(row, 0), H - 1) * pitch, x0, W);
     };
-    auto next_row = [&](int row) {  // row_ptr: row -> row + 1, clamped to the image
-        if (row >= 0 && row < H - 1) row_ptr += pitch;
-    };
 
     // one image row r enters: pack it; with kMedian the medians of row r-1 follow, with
     // kLaplacian the Laplacians of row r-2. The next row's word is requested before the
-    // arithmetic so that its latency hides behind it.
+    // arithmetic so that its latency hides behind it (two rows ahead: no gain). kInterior:
+    // rows r + 1 and r - 2 need no border rule (0 < r - 2 < H - 1, r + 1 <= H - 1).
     uint32_t g_next = load_row(y0 - 2);
-    auto step = [&](int r, auto median_tag, auto laplacian_tag) {
+    auto step = [&](int r, auto median_tag, auto laplacian_tag, auto interior_tag) {
         constexpr bool kMedian = decltype(median_tag)::value, kLaplacian = decltype(laplacian_tag)::value;
+        constexpr bool kInterior = decltype(interior_tag)::value;
         const uint32_t g = g_next;
-        next_row(r);
-        if (r <= y1) g_next = load_row(r + 1);
-        const uint32_t gr = __shfl_down_sync(0xffffffffu, g, 1);
+        if (kInterior) {
+            row_ptr += pitch;
+            g_next = load_row(r + 1);
+        } else {
+            if (r >= 0 && r < H - 1) row_ptr += pitch;  // row r -> r + 1, clamped to the image
+            if (r <= y1) g_next = load_row(r + 1);
+        }
         // zero-extended column pairs (x0,x0+1) (x0+1,x0+2) (x0+2,x0+3) (x0+3,x0+4); the pair
         // (x0-1,x0) is the left lane's fourth pair, so its sorted triple comes by shuffle
-        const uint32_t rz = gr & 255u;
         const uint32_t c1 = __byte_perm(g, 0u, 0x4140);
         const uint32_t c2 = __byte_perm(g, 0u, 0x4241);
         const uint32_t c3 = __byte_perm(g, 0u, 0x4342);
-        const uint32_t c4 = __byte_perm(rz, g, 0x2017);
+        const uint32_t c4 = __byte_perm(__shfl_down_sync(0xffffffffu, c1, 1), g, select_c4);
         if (kMedian) {
             // column pass on rows r-2, r-1, r
-            const uint32_t lo1 = min3x2(a1, b1, c1), hi1 = max3x2(a1, b1, c1), md1 = a1 + b1 + c1 - lo1 - hi1;
-            const uint32_t lo2 = min3x2(a2, b2, c2), hi2 = max3x2(a2, b2, c2), md2 = a2 + b2 + c2 - lo2 - hi2;
-            const uint32_t lo3 = min3x2(a3, b3, c3), hi3 = max3x2(a3, b3, c3), md3 = a3 + b3 + c3 - lo3 - hi3;
-            const uint32_t lo4 = min3x2(a4, b4, c4), hi4 = max3x2(a4, b4, c4), md4 = a4 + b4 + c4 - lo4 - hi4;
+            const uint32_t lo1 = min3x2(a1, b1, c1), hi1 = max3x2(a1, b1, c1), md1 = middle(a1, b1, c1, lo1, hi1);
+            const uint32_t lo2 = min3x2(a2, b2, c2), hi2 = max3x2(a2, b2, c2), md2 = middle(a2, b2, c2, lo2, hi2);
+            const uint32_t lo3 = min3x2(a3, b3, c3), hi3 = max3x2(a3, b3, c3), md3 = middle(a3, b3, c3, lo3, hi3);
+            const uint32_t lo4 = min3x2(a4, b4, c4), hi4 = max3x2(a4, b4, c4), md4 = middle(a4, b4, c4, lo4, hi4);
             const uint32_t lo0 = __shfl_up_sync(0xffffffffu, lo4, 1);
             const uint32_t md0 = __shfl_up_sync(0xffffffffu, md4, 1);
             const uint32_t hi0 = __shfl_up_sync(0xffffffffu, hi4, 1);
@@ -337,8 +394,8 @@ __global__ void __launch_bounds__(kPackedWarps * 32) focus_packed_kernel(const P
                 // Laplacian of row y = r-2: centre m1, up m2 (row r-3), down m (row r-1);
                 // reflect-101 at the top / bottom image rows
                 const int y = r - 2;
-                const uint32_t ua = y == 0 ? ma : m2a, ub = y == 0 ? mb : m2b;
-                const uint32_t da = y == H - 1 ? m2a : ma, db = y == H - 1 ? m2b : mb;
+                const uint32_t ua = !kInterior && y == 0 ? ma : m2a, ub = !kInterior && y == 0 ? mb : m2b;
+                const uint32_t da = !kInterior && y == H - 1 ? m2a : ma, db = !kInterior && y == H - 1 ? m2b : mb;
                 const uint32_t nl = __shfl_up_sync(0xffffffffu, m1b, 1);
                 const uint32_t nr = __shfl_down_sync(0xffffffffu, m1a, 1);
                 const uint32_t mid = __byte_perm(m1a, m1b, 0x5432);  // (m1, m2)
@@ -352,7 +409,8 @@ __global__ void __launch_bounds__(kPackedWarps * 32) focus_packed_kernel(const P
                 vb = max3x2(vb, bias, vb);
                 va = min3x2(va, top, va);
                 vb = min3x2(vb, top, vb);
-                const uint32_t l4 = __byte_perm(va, vb, 0x6420) & count_mask;
+                // every lane sums; the lanes that do not count drop theirs after the loop
+                const uint32_t l4 = __byte_perm(va, vb, 0x6420);
                 sum = __dp4a(l4, 0x01010101u, sum);
                 sum2 = __dp4a(l4, l4, sum2);
             }
@@ -364,23 +422,32 @@ __global__ void __launch_bounds__(kPackedWarps * 32) focus_packed_kernel(const P
     };
     using yes = std::true_type;
     using no = std::false_type;
-    step(y0 - 2, no{}, no{});
-    step(y0 - 1, no{}, no{});
-    step(y0, yes{}, no{});
-    step(y0 + 1, yes{}, no{});
+    step(y0 - 2, no{}, no{}, no{});
+    step(y0 - 1, no{}, no{}, no{});
+    step(y0, yes{}, no{}, no{});
+    step(y0 + 1, yes{}, no{}, no{});
+    step(y0 + 2, yes{}, yes{}, no{});  // the Laplacian of row y0: reflects upwards when y0 == 0
+    int r = y0 + 3;
 #pragma unroll 6
-    for (int r = y0 + 2; r <= y1 + 1; ++r) step(r, yes{}, yes{});
+    for (; r <= y1 - 2; ++r) step(r, yes{}, yes{}, yes{});
+    for (; r <= y1 + 1; ++r) step(r, yes{}, yes{}, no{});  // rows y1 - 1 .. y1 + 1 may lie below the image
 
-    for (int off = 16; off > 0; off >>= 1) {
-        sum += __shfl_down_sync(0xffffffffu, sum, off);
-        sum2 += __shfl_down_sync(0xffffffffu, sum2, off);
+    if (!counts) sum = sum2 = 0;
+    for (int off = 8; off > 0; off >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, off, 16);
+        sum2 += __shfl_down_sync(0xffffffffu, sum2, off, 16);
     }
-    if (lane == 0) {
+    const uint32_t upper = __shfl_down_sync(0xffffffffu, sum, 16), upper2 = __shfl_down_sync(0xffffffffu, sum2, 16);
+    if (!shared_tile) {
+        sum += upper;
+        sum2 += upper2;
+    }
+    if (lane == 0 || (shared_tile && valid && lane == 16)) {
         atomicAdd(&p.accum[2 * e], (unsigned long long)sum);
         atomicAdd(&p.accum[2 * e + 1], (unsigned long long)sum2);
         __threadfence();
         const unsigned int ticket = atomicAdd(&p.tickets[e], 1u);
-        if (ticket == (unsigned)tiles_per_env - 1) {
+        if (ticket == (unsigned)(p.segs * p.bands) - 1) {
             __threadfence();
             const unsigned long long S = atomicExch(&p.accum[2 * e], 0ull);
             const unsigned long long S2 = atomicExch(&p.accum[2 * e + 1], 0ull);

@@ -14,8 +14,14 @@ def main():
     from reinfocus_b200 import _lib
 
     ctx = _lib.shared_context()
+    only = None
+    if "--only" in sys.argv:  # --only <height> <envs>: one case (profiler captures)
+        at = sys.argv.index("--only")
+        only = (int(sys.argv[at + 1]), int(sys.argv[at + 2]))
     for height in (300, 600):
         for n in (1, 8, 64, 256, 1024, 4096):
+            if only and (height, n) != only:
+                continue
             if n * height * height > 2**31:
                 continue
             gray = torch.randint(0, 256, (n, height, height), dtype=torch.uint8, device="cuda")

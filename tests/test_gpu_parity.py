@@ -524,12 +524,15 @@ def test_focus_matches_oracle_and_cv2(torch, shape):
     numpy.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13)
 
 
-@pytest.mark.parametrize("shape", [(2, 8), (5, 8), (33, 12), (40, 116), (40, 120), (40, 124), (40, 128),
-                                   (37, 240), (64, 244), (31, 364), (300, 300), (75, 1200)])
+@pytest.mark.parametrize("shape", [(2, 8), (5, 8), (33, 12), (7, 56), (9, 60), (10, 64), (40, 116), (40, 120),
+                                   (40, 124), (40, 128), (12, 180), (37, 240), (64, 244), (31, 364),
+                                   (300, 300), (75, 1200)])
 @pytest.mark.parametrize("channels", [1, 3])
 def test_packed_focus_kernel_equals_staged_kernel_and_oracle(torch, shape, channels):
     """The warp-marching u16x2 kernel (W % 4 == 0) against the staged general kernel (A/B on
-    the device) and the oracle, gray and RGB input, widths around the 120-column tile."""
+    the device) and the oracle, gray and RGB input, widths around the 120-column tile and its
+    60-column half (a last segment that narrow is run for two envs per warp; three envs leave
+    the last upper half-warp without one)."""
 
     from reinfocus_b200 import _lib
 
@@ -559,9 +562,10 @@ def test_packed_focus_kernel_on_a_large_batch(torch):
     from reinfocus_b200 import vision
 
     rng = numpy.random.default_rng(11)
-    gray = rng.integers(0, 256, size=(700, 36, 300), dtype=numpy.uint8)
-    got = vision.focus_values_device(torch.from_numpy(gray).cuda()).cpu().numpy()
-    numpy.testing.assert_array_equal(got, oracle.focus_values_gray(gray))
+    gray = rng.integers(0, 256, size=(701, 36, 300), dtype=numpy.uint8)
+    for envs in (700, 701):  # even / odd: the 60-column segment pairs envs per warp
+        got = vision.focus_values_device(torch.from_numpy(gray[:envs]).cuda()).cpu().numpy()
+        numpy.testing.assert_array_equal(got, oracle.focus_values_gray(gray[:envs]))
 
 
 def test_packed_focus_kernel_tall_saturated_frames_in_a_large_batch(torch):
