@@ -336,7 +336,7 @@ int rf_selftest(rf_ctx *ctx, int which, int arg, int64_t *mismatches, void *stre
  * rf_focus the general staged kernel even when the specialised ones apply (A/B parity
  * tests). RF_OPT_TRACE_CONTEXTS = -1 (default), 0 or 2..8: pixels per thread of the
  * default-camera tracer (0 = the one-pixel-per-thread kernel, -1 = by batch size: 0 for one
- * or two 300 x 300 envs, then 4 and 8 pixels per thread in blocks of 64 to 224 threads);
+ * or two 300 x 300 envs, then 4 and 8 pixels per thread in blocks of 64 to 256 threads);
  * every setting produces the same bytes. */
 enum { RF_OPT_FORCE_GENERIC = 0, RF_OPT_TRACE_CONTEXTS = 1 };
 int rf_set_option(rf_ctx *ctx, int option, int value);
