@@ -556,6 +556,33 @@ def test_packed_focus_kernel_equals_staged_kernel_and_oracle(torch, shape, chann
         assert context.last_focus_kernel() == kernel
 
 
+def test_packed_focus_kernel_random_shapes(torch):
+    """60 random (envs, height, width, channels) cases around every tiling rule of the packed
+    kernel: 1 to 4 column segments, last segment wider or narrower than 60 columns (shared by
+    env pairs or not), odd and even batches, bands of 1 to H rows."""
+
+    from reinfocus_b200 import _lib
+
+    rng = numpy.random.default_rng(2024)
+    ctx = _lib.Context()
+    for case in range(60):
+        envs = int(rng.integers(1, 10))
+        height = int(rng.integers(2, 90))
+        width = 4 * int(rng.integers(2, 110))
+        channels = (1, 3)[case % 2]
+        imgs = rng.integers(0, 256, size=(envs, height, width, 3), dtype=numpy.uint8)
+        if case % 3 == 0:  # piecewise-constant content: medians keep the edges, Laplacian saturates
+            imgs = numpy.repeat(numpy.repeat(imgs[:, ::3, ::4], 3, axis=1), 4, axis=2)[:, :height, :width]
+            imgs = numpy.ascontiguousarray(imgs)
+        data = imgs if channels == 3 else oracle.gray(imgs)
+        want = oracle.focus_values(imgs) if channels == 3 else oracle.focus_values_gray(data)
+        dev = torch.from_numpy(data).cuda()
+        out = torch.zeros(envs, dtype=torch.float64, device="cuda")
+        ctx.focus(envs, height, width, dev.data_ptr(), channels, out.data_ptr())
+        assert ctx.last_focus_kernel() == 1
+        numpy.testing.assert_array_equal(out.cpu().numpy(), want, err_msg=f"{envs} x {height} x {width} x {channels}")
+
+
 def test_packed_focus_kernel_on_a_large_batch(torch):
     """4096-env-like launch shape at reduced height: many envs, grid.y > tiles."""
 
