@@ -560,7 +560,7 @@ def issue_view(traffic, n_local, trace_ms, sm_count, clock_summary):
     peak = sm_count * 4 * mhz * 1e6 / 1e9
     return {"warp_inst_per_launch": per_env * n_local, "achieved": achieved, "peak": peak,
             "unit": "G warp-inst/s", "frac": achieved / peak,
-            "source": "static ncu capture: smsp__inst_executed.sum per env at 256 envs "
+            "source": "static ncu capture: smsp__inst_executed.sum per env at 4096 envs "
                       "(profiles/ncu_traffic.json); peak = SMs x 4 schedulers x sampled SM clock",
             "ncu_pct": traffic.get("trace_kernel_ncu_pct")}
 
@@ -576,8 +576,8 @@ def alu_view(traffic, n_local, trace_ms, sm_count, clock_summary, key="trace_ker
     return {"warp_inst_per_launch": per_env * n_local, "achieved": achieved, "peak": peak,
             "unit": "G ALU-pipe warp-inst/s", "frac": achieved / peak,
             "source": source or
-                      "static ncu capture: executed LOP3 / SHF / IADD3 / ISETP / FSETP ... per env at 256 envs "
-                      "(profiles/r02/mp8_opcode_mix.txt); peak = SMs x 4 schedulers x sampled SM clock / 2 "
+                      "static ncu capture: executed LOP3 / SHF / IADD3 / ISETP / FSETP ... per env at 4096 envs "
+                      "(profiles/r02/final_4096envs_opcode_mix.txt); peak = SMs x 4 schedulers x sampled SM clock / 2 "
                       "(measured: tools/pipe_microbench.cu, 2.0 clocks per warp instruction)"}
 
 

@@ -1,7 +1,8 @@
 # Profiles the two hot kernels with Nsight Compute on one B200 (run under gpurun).
-# usage: bash scripts/gpu_profile.sh <tag>   -> gpurun_out/<tag>_*
+# usage: bash scripts/gpu_profile.sh <tag> [envs]   -> gpurun_out/<tag>_*
 TAG=${1:-prof}
-ARGS="--envs 256 --steps 2 --warmup 3 --no-cpu-baseline --no-reference-baselines"
+ENVS=${2:-256}
+ARGS="--envs $ENVS --steps 2 --warmup 3 --no-cpu-baseline --no-reference-baselines"
 mkdir -p gpurun_out
 python bench.py $ARGS > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py $ARGS > gpurun_out/${TAG}_ncu1.log 2>&1
